@@ -1,0 +1,4 @@
+from .rbbox_nms import (multiclass_nms, multiclass_nms_with_index, multiclass_thetaobb_nms,
+                        thetaobb_nms_by_bbox_nms)
+
+__all__ = ['multiclass_nms', 'multiclass_nms_with_index', 'multiclass_thetaobb_nms', 'thetaobb_nms_by_bbox_nms']

@@ -1,0 +1,120 @@
+"""Multi-class NMS drivers, one kernel pass over all classes.
+
+Mirrors mmdet/core/post_processing/bbox_nms.py:6-76 (`multiclass_nms`) and
+rbbox_nms.py:6-62,64-119 (`multiclass_nms_with_index`, `thetaobb_nms_by_bbox_nms`), and
+provides `multiclass_thetaobb_nms`, the call the reference left commented out
+(mmdet/models/bbox_heads/rbbox_head.py:294-295).  The per-class Python loop and the
+class-offset trick are both replaced by group ids handed to the batched kernel.
+"""
+import torch
+
+from ...ops import functional as F
+from ...ops.nms import nms_wrapper
+
+
+def _select(multi_boxes, multi_scores, score_thr, dim):
+    """score filter -> (boxes (m,dim), scores (m,), labels (m,), row index (m,)), class-major order."""
+    num_classes = multi_scores.size(1) - 1
+    if multi_boxes.shape[1] > dim:
+        boxes = multi_boxes.view(multi_scores.size(0), -1, dim)[:, 1:]
+    else:
+        boxes = multi_boxes[:, None].expand(-1, num_classes, dim)
+    scores = multi_scores[:, 1:]
+    valid = (scores > score_thr).t()                  # (C, n): class-major like the reference's loop
+    labels, rows = valid.nonzero(as_tuple=True)
+    return boxes[rows, labels], scores[rows, labels], labels, rows
+
+
+def _finish(dets, labels, max_num):
+    if max_num > 0 and dets.shape[0] > max_num:       # rbbox_nms.py:52-57 / bbox_nms.py:69-76
+        _, inds = dets[:, -1].sort(descending=True)
+        inds = inds[:max_num]
+        dets, labels = dets[inds], labels[inds]
+    return dets, labels
+
+
+def _multiclass(multi_boxes, multi_scores, score_thr, iou_thr, max_num, dim, plus_one):
+    boxes, scores, labels, _ = _select(multi_boxes, multi_scores, score_thr, dim)
+    if boxes.numel() == 0:
+        return multi_boxes.new_zeros((0, dim + 1)), multi_boxes.new_zeros((0, ), dtype=torch.long)
+    num_classes = multi_scores.size(1) - 1
+    keep = F.nms_batched(boxes, scores, labels, iou_thr, n_groups=num_classes, cmp_ge=False, plus_one=plus_one)
+    dets = torch.cat([boxes[keep], scores[keep, None]], dim=1)
+    return _finish(dets, labels[keep], max_num)
+
+
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None):
+    """mmdet/core/post_processing/bbox_nms.py:6-76.  Returns (bboxes (k,5), labels (k,)), labels 0-based."""
+    cfg = nms_cfg.copy()
+    nms_type = cfg.pop('type', 'nms')
+    if nms_type != 'nms':
+        raise NotImplementedError('multiclass_nms supports type="nms" only (got %r)' % nms_type)
+    if score_factors is not None:
+        multi_scores = torch.cat([multi_scores[:, :1], multi_scores[:, 1:] * score_factors[:, None]], dim=1)
+    return _multiclass(multi_bboxes, multi_scores, score_thr, cfg.get('iou_thr', 0.5), max_num, 4, plus_one=True)
+
+
+def multiclass_thetaobb_nms(multi_rbboxes, multi_scores, score_thr, polygon_nms_iou_thr, max_num=-1,
+                            out_dim_reg=5):
+    """Rotated multi-class NMS (rbbox_head.py:294-295 call shape).
+
+    multi_rbboxes (n, C*d) or (n, d), d = out_dim_reg (5 theta-OBB, 8 point-OBB);
+    multi_scores (n, C+1) with the background in column 0.
+    Returns (rbboxes (k, d+1), labels (k,)), labels 0-based, class-major then top-`max_num` by score.
+    """
+    return _multiclass(multi_rbboxes, multi_scores, score_thr, polygon_nms_iou_thr, max_num, out_dim_reg,
+                       plus_one=False)
+
+
+def multiclass_nms_with_index(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1):
+    """mmdet/core/post_processing/rbbox_nms.py:6-62: also returns per-class masks and keep indices."""
+    cfg = nms_cfg.copy()
+    nms_type = cfg.pop('type', 'nms')
+    if nms_type != 'nms':
+        raise NotImplementedError('multiclass_nms_with_index supports type="nms" only (got %r)' % nms_type)
+    num_classes = multi_scores.shape[1]
+    valid = multi_scores[:, 1:] > score_thr
+    bbox_cls_inds = [valid[:, i] for i in range(num_classes - 1)]
+    boxes, scores, labels, _ = _select(multi_bboxes, multi_scores, score_thr, 4)
+    if boxes.numel() == 0:
+        return (multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0, ), dtype=torch.long), bbox_cls_inds, [])
+    keep = F.nms_batched(boxes, scores, labels, cfg.get('iou_thr', 0.5), n_groups=num_classes - 1, cmp_ge=False,
+                         plus_one=True)
+    # per-class keep indices, relative to that class's filtered subset (what nms_op returned at rbbox_nms.py:43-44)
+    counts = torch.bincount(labels, minlength=num_classes - 1)
+    starts = torch.cumsum(counts, 0) - counts
+    kept_labels = labels[keep]
+    bbox_keep_inds = []
+    for c in range(num_classes - 1):
+        if counts[c] == 0:
+            continue
+        bbox_keep_inds.append(keep[kept_labels == c] - starts[c])
+    dets = torch.cat([boxes[keep], scores[keep, None]], dim=1)
+    dets, out_labels = _finish(dets, kept_labels, max_num)
+    return dets, out_labels, bbox_cls_inds, bbox_keep_inds
+
+
+def thetaobb_nms_by_bbox_nms(multi_bboxes, multi_scores, bbox_cls_inds, bbox_keep_inds, max_num=-1, out_dim_reg=5):
+    """mmdet/core/post_processing/rbbox_nms.py:64-119: gather OBBs with the keep indices of the HBB NMS."""
+    num_classes = multi_scores.shape[1]
+    bboxes, labels = [], []
+    keep_iter = iter(bbox_keep_inds)
+    for i in range(1, num_classes):
+        cls_inds = bbox_cls_inds[i - 1]
+        if not cls_inds.any():
+            continue
+        if multi_bboxes.shape[1] == out_dim_reg:
+            _bboxes = multi_bboxes[cls_inds, :]
+        else:
+            _bboxes = multi_bboxes[cls_inds, i * out_dim_reg:(i + 1) * out_dim_reg]
+        cls_dets = torch.cat([_bboxes, multi_scores[cls_inds, i][:, None]], dim=1)
+        cls_dets = cls_dets[next(keep_iter), :]
+        bboxes.append(cls_dets)
+        labels.append(multi_bboxes.new_full((cls_dets.shape[0], ), i - 1, dtype=torch.long))
+    if bboxes:
+        return _finish(torch.cat(bboxes), torch.cat(labels), max_num)
+    return multi_bboxes.new_zeros((0, out_dim_reg + 1)), multi_bboxes.new_zeros((0, ), dtype=torch.long)
+
+
+__all__ = ['multiclass_nms', 'multiclass_thetaobb_nms', 'multiclass_nms_with_index', 'thetaobb_nms_by_bbox_nms',
+           'nms_wrapper']

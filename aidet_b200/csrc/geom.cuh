@@ -1,0 +1,244 @@
+// geom.cuh -- pairwise overlap arithmetic for oriented boxes (FP32, registers only).
+//
+// What it replaces: the polygon IoU that AIDet reaches only through the external
+// wwtool.mergebypoly_mp (mmdet/datasets/dota.py:336) and the commented
+// nms_wrapper.thetaobb_nms slot (mmdet/core/post_processing/rbbox_nms.py:97);
+// HBB overlap follows mmdet/ops/nms/src/nms_kernel.cu:14-22 (+1 convention).
+//
+// Formulation (B200-first, not a translation of Sutherland-Hodgman): clipping
+// a polygon A against a box B is written as a line integral over A's edges
+// (Green's theorem with Q(x,y) = clamp(x,-W,W) * 1[|y|<=H] in B's frame):
+//
+//     area(A ^ B) = sum over CCW edges (p -> p+d) of
+//                   dy * Integral_{t0}^{t1} clamp(px + t dx, -W, W) dt
+//
+// where [t0,t1] is the part of the edge inside the slab |y| <= H.  Every term
+// is a closed form of min/max/fma: no vertex lists, no data-dependent trip
+// counts, no local memory, and no topological decisions that could flip the
+// result by O(1) -- each edge integral is continuous in its inputs.
+// General (8-point) quads use the same idea per triangle of a fan of B in
+// affine coordinates: Q = clamp(xi, 0, 1-eta) * 1[0<=eta<=1].
+//
+// The header is host+device so tests/ can compile the very same arithmetic
+// with g++ and check it against the float64 oracle without a GPU.  It is NOT a
+// CPU fallback: the product only ever calls it from kernels.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define AIDET_HD __host__ __device__ __forceinline__
+#define AIDET_ALIGN16 __align__(16)
+#else
+#define AIDET_HD static inline
+#define AIDET_ALIGN16 alignas(16)
+#endif
+
+namespace aidet {
+
+#if defined(__CUDA_ARCH__)
+AIDET_HD float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }  // MUFU.RCP, <= 1 ulp
+AIDET_HD float fdiv(float a, float b) { return __fdividef(a, b); }
+#else
+AIDET_HD float frcp(float x) { return 1.0f / x; }
+AIDET_HD float fdiv(float a, float b) { return a / b; }
+#endif
+
+enum { MODE_IOU = 0, MODE_IOF = 1 };
+
+// ---------------------------------------------------------------- records
+// theta-OBB, prepared once per box by the prologue kernel (32 B each).
+struct AIDET_ALIGN16 RectRow {   // the box that is transformed ("A")
+  float cx, cy;                  // centre
+  float ux, uy;                  // half-axis  (w/2)( cos,  sin)
+  float vx, vy;                  // half-axis  (h/2)(-sin,  cos)
+  float area, rad;               // w*h, circumradius
+};
+struct AIDET_ALIGN16 RectCol {   // the box whose frame is used ("B")
+  float cx, cy;
+  float c, s;                    // cos, sin
+  float W, H;                    // half extents
+  float area, rad;
+};
+
+// point-OBB (general simple quad), 64 B each.
+struct AIDET_ALIGN16 QuadRow {
+  float x[4], y[4];              // CCW
+  float area, rad, mx, my;       // |area|, bounding radius about (mx,my)
+  float pad[4];
+};
+struct AIDET_ALIGN16 QuadCol {
+  float ox, oy;                  // b0
+  float e1x, e1y, e2x, e2y, e3x, e3y;   // b1-b0, b2-b0, b3-b0
+  float invD1, invD2;            // 1/(e1 x e2), 1/(e2 x e3)   (0 if degenerate)
+  float aD1, aD2;                // |e1 x e2|, |e2 x e3|
+  float area, rad, mx, my;
+};
+
+// axis-aligned box (x1,y1,x2,y2) with the legacy +1 folded into `one`.
+struct AIDET_ALIGN16 HbbBox { float x1, y1, x2, y2; };
+
+// ------------------------------------------------- rect ^ rect (theta-OBB)
+
+// Edge integral described in the header comment, for the edge p + t d, t in [0,1].
+//   rdx, rdy : 1/dx, 1/dy of the (tiny-guarded) edge vector
+//   Ws, Hs   : copysign(W, dx), copysign(H, dy) -- orders the slab crossings so
+//              that no min/max is needed to sort them
+// The in-slab parameter range [t0,t1] is split at the x = -+W crossings into a
+// "before" piece (clamp value -Ws), an inside piece (value = x at its middle)
+// and an "after" piece (value +Ws).  All piece lengths are max(0, .) of
+// differences, so an empty range contributes exactly 0 without a branch.
+AIDET_HD float rect_edge(float px, float py, float hdx, float dy, float rdx, float rdy, float Ws, float Hs) {
+  float t0 = fmaxf((-Hs - py) * rdy, 0.0f);
+  float t1 = fminf((Hs - py) * rdy, 1.0f);
+  float xa = (-Ws - px) * rdx, xb = (Ws - px) * rdx;      // xa <= xb
+  float i0 = fmaxf(t0, xa), i1 = fminf(t1, xb);
+  float tin = fmaxf(i1 - i0, 0.0f);
+  float tbe = fmaxf(fminf(t1, xa) - t0, 0.0f);
+  float taf = fmaxf(t1 - fmaxf(t0, xb), 0.0f);
+  float xmid = fmaf(hdx, i0 + i1, px);
+  return dy * fmaf(Ws, taf - tbe, tin * xmid);
+}
+
+AIDET_HD float guard_tiny(float d) { return (fabsf(d) > 1e-18f) ? d : 1e-18f; }
+
+// Intersection area of A (row record) with B (col record).
+AIDET_HD float rect_inter(const RectRow& a, const RectCol& b) {
+  float relx = a.cx - b.cx, rely = a.cy - b.cy;
+  // rotate by -theta_b
+  float rx = fmaf(b.c, relx, b.s * rely), ry = fmaf(b.c, rely, -b.s * relx);
+  float ux = guard_tiny(fmaf(b.c, a.ux, b.s * a.uy)), uy = guard_tiny(fmaf(b.c, a.uy, -b.s * a.ux));
+  float vx = guard_tiny(fmaf(b.c, a.vx, b.s * a.vy)), vy = guard_tiny(fmaf(b.c, a.vy, -b.s * a.vx));
+  // corners p0 = r-u-v, p1 = r+u-v, p3 = r-u+v  (CCW: p0,p1,p2,p3)
+  float mx = rx - ux, my = ry - uy;
+  float p0x = mx - vx, p0y = my - vy;
+  float p3x = mx + vx, p3y = my + vy;
+  float p1x = (rx + ux) - vx, p1y = (ry + uy) - vy;
+  // edge vectors are +-2u, +-2v:  1/(2u) = 0.5/u, half of dx = u
+  float rux = 0.5f * frcp(ux), ruy = 0.5f * frcp(uy), rvx = 0.5f * frcp(vx), rvy = 0.5f * frcp(vy);
+  float Wu = copysignf(b.W, ux), Hu = copysignf(b.H, uy), Wv = copysignf(b.W, vx), Hv = copysignf(b.H, vy);
+  // edges p0->p1 (+2u), p1->p2 (+2v), p2->p3 == -(p3->p2, +2u), p3->p0 == -(p0->p3, +2v)
+  float su = rect_edge(p0x, p0y, ux, uy, rux, ruy, Wu, Hu) - rect_edge(p3x, p3y, ux, uy, rux, ruy, Wu, Hu);
+  float sv = rect_edge(p1x, p1y, vx, vy, rvx, rvy, Wv, Hv) - rect_edge(p0x, p0y, vx, vy, rvx, rvy, Wv, Hv);
+  return 2.0f * (su + sv);       // dy was passed as half the edge's dy
+}
+
+AIDET_HD float finish_overlap(float inter, float area_a, float area_b, int mode) {
+  inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_b));
+  float den = (mode == MODE_IOF) ? area_a : (area_a + area_b - inter);
+  return den > 0.0f ? fdiv(inter, den) : 0.0f;
+}
+
+AIDET_HD float rect_overlap(const RectRow& a, const RectCol& b, int mode) {
+  float dx = a.cx - b.cx, dy = a.cy - b.cy, r = a.rad + b.rad;
+  if (fmaf(dx, dx, dy * dy) > r * r) return 0.0f;       // disjoint bounding circles
+  return finish_overlap(rect_inter(a, b), a.area, b.area, mode);
+}
+
+// prologue math (runs once per box; double keeps sin/cos at <= 0.5 ulp)
+AIDET_HD void rect_prepare(const float* box5, RectRow* row, RectCol* col) {
+  float cx = box5[0], cy = box5[1], w = fabsf(box5[2]), h = fabsf(box5[3]);
+  double th = (double)box5[4];
+  float c = (float)cos(th), s = (float)sin(th);
+  float W = 0.5f * w, H = 0.5f * h;
+  float rad = sqrtf(W * W + H * H) * 1.000001f + 1e-6f;
+  if (row) { row->cx = cx; row->cy = cy; row->ux = W * c; row->uy = W * s; row->vx = -H * s; row->vy = H * c;
+             row->area = w * h; row->rad = rad; }
+  if (col) { col->cx = cx; col->cy = cy; col->c = c; col->s = s; col->W = W; col->H = H;
+             col->area = w * h; col->rad = rad; }
+}
+
+// --------------------------------------------- quad ^ quad (point-OBB, general)
+
+// mean over t in [0,1] of max(f0 + t (f1-f0), 0)
+AIDET_HD float mean_pos(float f0, float f1) {
+  float p0 = fmaxf(f0, 0.0f), p1 = fmaxf(f1, 0.0f);
+  float df = f1 - f0;
+  float rho = (fabsf(df) > 1e-20f) ? (p1 - p0) * frcp(df) : 1.0f;
+  return 0.5f * (p0 + p1) * rho;
+}
+
+// edge integral in a triangle's affine frame: Q = clamp(xi,0,1-eta) 1[0<=eta<=1]
+AIDET_HD float tri_edge(float xp, float ep, float xq, float eq) {
+  float de = eq - ep, dx = xq - xp;
+  float rde = frcp(de);
+  float ta = -ep * rde, tb = (1.0f - ep) * rde;
+  float t0 = fmaxf(fminf(ta, tb), 0.0f);
+  float t1 = fminf(fmaxf(ta, tb), 1.0f);
+  float x0 = fmaf(t0, dx, xp), x1 = fmaf(t1, dx, xp);
+  float n0 = fminf(fmaxf(fmaf(t0, de, ep), 0.0f), 1.0f), n1 = fminf(fmaxf(fmaf(t1, de, ep), 0.0f), 1.0f);
+  float v = mean_pos(x0, x1) - mean_pos(x0 - (1.0f - n0), x1 - (1.0f - n1));
+  v = de * (t1 - t0) * v;
+  return (t1 > t0 && fabsf(de) > 1e-20f) ? v : 0.0f;
+}
+
+AIDET_HD float quad_tri_inter(const QuadRow& a, float ox, float oy, float e1x, float e1y, float e2x, float e2y,
+                              float invD, float aD) {
+  float xi[4], et[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float px = a.x[k] - ox, py = a.y[k] - oy;
+    xi[k] = (px * e2y - py * e2x) * invD;
+    et[k] = (e1x * py - e1y * px) * invD;
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) s += tri_edge(xi[k], et[k], xi[(k + 1) & 3], et[(k + 1) & 3]);
+  return aD * s;
+}
+
+AIDET_HD float quad_inter(const QuadRow& a, const QuadCol& b) {
+  return quad_tri_inter(a, b.ox, b.oy, b.e1x, b.e1y, b.e2x, b.e2y, b.invD1, b.aD1)
+       + quad_tri_inter(a, b.ox, b.oy, b.e2x, b.e2y, b.e3x, b.e3y, b.invD2, b.aD2);
+}
+
+AIDET_HD float quad_overlap(const QuadRow& a, const QuadCol& b, int mode) {
+  float dx = a.mx - b.mx, dy = a.my - b.my, r = a.rad + b.rad;
+  if (fmaf(dx, dx, dy * dy) > r * r) return 0.0f;
+  return finish_overlap(quad_inter(a, b), a.area, b.area, mode);
+}
+
+AIDET_HD void quad_prepare(const float* box8, QuadRow* row, QuadCol* col) {
+  float x[4], y[4];
+  for (int k = 0; k < 4; k++) { x[k] = box8[2 * k]; y[k] = box8[2 * k + 1]; }
+  // signed area about p0 (translation keeps the products small)
+  float ax = x[1] - x[0], ay = y[1] - y[0], bx = x[2] - x[0], by = y[2] - y[0], cx = x[3] - x[0], cy = y[3] - y[0];
+  float sa = 0.5f * ((ax * by - ay * bx) + (bx * cy - by * cx));
+  if (sa < 0.0f) {  // make CCW: swap p1 <-> p3
+    float t = x[1]; x[1] = x[3]; x[3] = t; t = y[1]; y[1] = y[3]; y[3] = t;
+    t = ax; ax = cx; cx = t; t = ay; ay = cy; cy = t;
+  }
+  float area = fabsf(sa);
+  float mx = 0.25f * (x[0] + x[1] + x[2] + x[3]), my = 0.25f * (y[0] + y[1] + y[2] + y[3]);
+  float r2 = 0.0f;
+  for (int k = 0; k < 4; k++) { float dx = x[k] - mx, dy = y[k] - my; r2 = fmaxf(r2, dx * dx + dy * dy); }
+  float rad = sqrtf(r2) * 1.000001f + 1e-5f * (fabsf(mx) + fabsf(my)) + 1e-6f;
+  if (row) {
+    for (int k = 0; k < 4; k++) { row->x[k] = x[k]; row->y[k] = y[k]; }
+    row->area = area; row->rad = rad; row->mx = mx; row->my = my;
+    row->pad[0] = row->pad[1] = row->pad[2] = row->pad[3] = 0.0f;
+  }
+  if (col) {
+    col->ox = x[0]; col->oy = y[0];
+    col->e1x = ax; col->e1y = ay; col->e2x = bx; col->e2y = by; col->e3x = cx; col->e3y = cy;
+    float D1 = ax * by - ay * bx, D2 = bx * cy - by * cx;
+    col->invD1 = (fabsf(D1) > 1e-20f) ? 1.0f / D1 : 0.0f; col->aD1 = (fabsf(D1) > 1e-20f) ? fabsf(D1) : 0.0f;
+    col->invD2 = (fabsf(D2) > 1e-20f) ? 1.0f / D2 : 0.0f; col->aD2 = (fabsf(D2) > 1e-20f) ? fabsf(D2) : 0.0f;
+    col->area = area; col->rad = rad; col->mx = mx; col->my = my;
+  }
+}
+
+// ------------------------------------------------------------- HBB (+1)
+
+// mmdet/ops/nms/src/nms_kernel.cu:14-22 (devIoU) / nms_cpu.cpp:47-55
+AIDET_HD float hbb_overlap(const HbbBox& a, const HbbBox& b, float one, int mode) {
+  float left = fmaxf(a.x1, b.x1), right = fminf(a.x2, b.x2);
+  float top = fmaxf(a.y1, b.y1), bottom = fminf(a.y2, b.y2);
+  float w = fmaxf(right - left + one, 0.f), h = fmaxf(bottom - top + one, 0.f);
+  float inter = w * h;
+  float sa = (a.x2 - a.x1 + one) * (a.y2 - a.y1 + one);
+  float sb = (b.x2 - b.x1 + one) * (b.y2 - b.y1 + one);
+  float den = (mode == MODE_IOF) ? sa : (sa + sb - inter);
+  return inter / den;
+}
+
+}  // namespace aidet

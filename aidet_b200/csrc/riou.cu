@@ -1,0 +1,234 @@
+// riou.cu -- pairwise rotated-IoU matrix / aligned pairs on sm_100a.
+//
+// Replaces (reference): the (m,n) overlap API of mmdet/core/bbox/geometry.py:4-88 for
+// oriented boxes, whose arithmetic AIDet only reaches through wwtool
+// (mmdet/datasets/dota.py:23,336).
+//
+// Layout / schedule:
+//   prologue  : one thread per box -> 32 B (theta-OBB) or 64 B (point-OBB) records in
+//               the caller's workspace: "row" records (the box that gets transformed)
+//               and "col" records (the box whose frame is used), see geom.cuh.
+//   main      : persistent CTAs of 256 threads.  A tile is TR rows x 256 columns; each
+//               lane keeps ONE column record in registers and walks the row records,
+//               which a single thread stages into shared memory with a 1-D TMA bulk
+//               copy (cp.async.bulk + mbarrier, double buffered) so the copy of tile
+//               t+1 overlaps the arithmetic of tile t.  Row records are read from
+//               shared memory with warp-uniform 128-bit loads (broadcast); the result
+//               row segment of a warp is one 128 B coalesced streaming store.
+//   bound     : FP32 issue (about 170 instructions per pair, no tensor-core shape);
+//               output traffic 4 B/pair is ~1/6 of HBM peak at full ALU rate.
+#include <type_traits>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace aidet {
+
+struct RectKind {
+  using Row = RectRow; using Col = RectCol;
+  static constexpr int FMT = 5;
+  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return rect_inter(a, b); }
+  __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { rect_prepare(p, r, c); }
+  template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.cx; }
+  template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.cy; }
+};
+struct QuadKind {
+  using Row = QuadRow; using Col = QuadCol;
+  static constexpr int FMT = 8;
+  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return quad_inter(a, b); }
+  __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { quad_prepare(p, r, c); }
+  template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.mx; }
+  template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.my; }
+};
+
+// SWAP = false: matrix-row boxes are staged as Row records, matrix-column boxes live in
+// registers as Col records (frame = column box).  SWAP = true (IoF): the frame is the
+// matrix-row box, whose area is the denominator, which bounds the error by ~2 ulp of it.
+template <class K, bool SWAP>
+struct PairOp {
+  using S = typename std::conditional<SWAP, typename K::Col, typename K::Row>::type;   // staged (matrix row)
+  using R = typename std::conditional<SWAP, typename K::Row, typename K::Col>::type;   // registers (matrix col)
+  __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) {
+    float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
+    if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;
+    float inter;
+    if constexpr (SWAP) inter = K::inter(r, s); else inter = K::inter(s, r);
+    return finish_overlap(inter, s.area, r.area, mode);
+  }
+};
+
+template <class K>
+__global__ void __launch_bounds__(256) riou_prepare_kernel(const float* __restrict__ boxes, int n,
+                                                           typename K::Row* rows, typename K::Col* cols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float b[K::FMT];
+#pragma unroll
+  for (int k = 0; k < K::FMT; k++) b[k] = boxes[(size_t)i * K::FMT + k];
+  typename K::Row r; typename K::Col c;
+  K::prepare(b, rows ? &r : nullptr, cols ? &c : nullptr);
+  if (rows) rows[i] = r;
+  if (cols) cols[i] = c;
+}
+
+constexpr int kColsPerTile = 256;
+constexpr int kMaxTileRows = 64;
+
+template <class K, bool SWAP>
+__global__ void __launch_bounds__(kColsPerTile)
+riou_matrix_kernel(const typename PairOp<K, SWAP>::S* __restrict__ rows, int m,
+                   const typename PairOp<K, SWAP>::R* __restrict__ cols, int n, int mode,
+                   float* __restrict__ out, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
+                   int tiles_per_cta) {
+  using P = PairOp<K, SWAP>;
+  using S = typename P::S; using R = typename P::R;
+  __shared__ __align__(128) S stage[2][kMaxTileRows];
+  __shared__ __align__(8) uint64_t bar[2];
+
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(t_begin + tiles_per_cta, n_tiles);
+  if (t_begin >= t_end) return;
+
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+  __syncthreads();
+
+  auto issue = [&](int t, int buf) {      // thread 0 only
+    int rt = t % n_row_tiles;
+    int r0 = rt * tile_rows;
+    uint32_t bytes = (uint32_t)(min(tile_rows, m - r0) * (int)sizeof(S));
+    mbar_expect_tx(&bar[buf], bytes);
+    tma_load_1d(&stage[buf][0], rows + r0, bytes, &bar[buf]);
+  };
+  if (threadIdx.x == 0) issue(t_begin, 0);
+
+  int cur_ct = -1;
+  R me;
+  bool live = false;
+  int col = 0;
+  for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && t + 1 < t_end) issue(t + 1, buf ^ 1);
+    const int ct = t / n_row_tiles, rt = t % n_row_tiles;
+    if (ct != cur_ct) {
+      cur_ct = ct;
+      col = ct * kColsPerTile + threadIdx.x;
+      live = col < n;
+      me = cols[live ? col : n - 1];
+    }
+    mbar_wait(&bar[buf], (it >> 1) & 1);
+    const int r0 = rt * tile_rows;
+    const int nr = min(tile_rows, m - r0);
+    float* o = out + (long long)r0 * ld + col;
+#pragma unroll 2
+    for (int r = 0; r < nr; ++r) {
+      S s = stage[buf][r];
+      float v = P::overlap(s, me, mode);
+      if (live) __stcs(o + (long long)r * ld, v);
+    }
+    __syncthreads();      // everyone is done with stage[buf] before it is refilled
+  }
+}
+
+template <class K>
+__global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                           int n, int mode, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float pa[K::FMT], pb[K::FMT];
+#pragma unroll
+  for (int k = 0; k < K::FMT; k++) { pa[k] = a[(size_t)i * K::FMT + k]; pb[k] = b[(size_t)i * K::FMT + k]; }
+  // frame = the box whose area is the denominator in IoF mode (a); symmetric for IoU
+  typename K::Row r; typename K::Col c;
+  K::prepare(pb, &r, nullptr);
+  K::prepare(pa, nullptr, &c);
+  out[i] = PairOp<K, true>::overlap(c, r, mode);
+}
+
+template <class K, bool SWAP>
+static int launch_matrix(const float* a, int m, const float* b, int n, int mode, float* out, long long ld,
+                         void* ws, int device, cudaStream_t s) {
+  using P = PairOp<K, SWAP>;
+  using S = typename P::S; using R = typename P::R;
+  S* rows = reinterpret_cast<S*>(ws);
+  R* cols = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)m * sizeof(S), 128));
+  if constexpr (SWAP) {
+    riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(a, m, nullptr, rows);
+    riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(b, n, cols, nullptr);
+  } else {
+    riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(a, m, rows, nullptr);
+    riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(b, n, nullptr, cols);
+  }
+  const int sms = sm_count(device);
+  const int n_col_tiles = ceil_div(n, kColsPerTile);
+  int tile_rows = kMaxTileRows;
+  while (tile_rows > 8 && (long long)ceil_div(m, tile_rows) * n_col_tiles < 8LL * sms) tile_rows >>= 1;
+  const int n_row_tiles = ceil_div(m, tile_rows);
+  const long long n_tiles_ll = (long long)n_row_tiles * n_col_tiles;
+  if (n_tiles_ll > 0x7fffffffLL) { set_error("riou: problem too large (%lld tiles)", n_tiles_ll); return AIDET_EINVAL; }
+  const int n_tiles = (int)n_tiles_ll;
+  // enough resident CTAs to fill the machine, contiguous tile ranges per CTA so the column
+  // record stays in registers across consecutive row tiles
+  int grid = min(n_tiles, sms * 8);
+  int tiles_per_cta = ceil_div(n_tiles, grid);
+  grid = ceil_div(n_tiles, tiles_per_cta);
+  {
+    ProfScope prof(PROF_RIOU, s);
+    riou_matrix_kernel<K, SWAP><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, mode, out, ld, tile_rows,
+                                                              n_row_tiles, n_tiles, tiles_per_cta);
+  }
+  count_launch(3);
+  AIDET_CUDA(cudaGetLastError());
+  return AIDET_OK;
+}
+
+}  // namespace aidet
+
+using namespace aidet;
+
+extern "C" {
+
+size_t aidet_riou_workspace_bytes(int m, int n, int fmt) {
+  size_t rec = (fmt == 8) ? 64 : 32;
+  return align_up((size_t)(m > 0 ? m : 0) * rec, 128) + align_up((size_t)(n > 0 ? n : 0) * rec, 128) + 128;
+}
+
+int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt, int mode, float* out,
+                          long long ld_out, void* workspace, size_t ws_bytes, int device, void* stream) {
+  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_matrix_f32: fmt must be 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_matrix_f32: bad mode %d", mode);
+  AIDET_REQUIRE(m >= 0 && n >= 0, "aidet_riou_matrix_f32: negative size");
+  if (m == 0 || n == 0) return AIDET_OK;
+  AIDET_REQUIRE(a && b && out && workspace, "aidet_riou_matrix_f32: null pointer");
+  AIDET_REQUIRE(ld_out >= n, "aidet_riou_matrix_f32: ld_out %lld < n %d", ld_out, n);
+  AIDET_REQUIRE(((uintptr_t)workspace & 15) == 0, "aidet_riou_matrix_f32: workspace must be 16 B aligned");
+  if (ws_bytes < aidet_riou_workspace_bytes(m, n, fmt)) {
+    set_error("aidet_riou_matrix_f32: workspace %zu < %zu", ws_bytes, aidet_riou_workspace_bytes(m, n, fmt));
+    return AIDET_EWORKSPACE;
+  }
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (fmt == 5) {
+    return mode == AIDET_MODE_IOF ? launch_matrix<RectKind, true>(a, m, b, n, mode, out, ld_out, workspace, device, s)
+                                  : launch_matrix<RectKind, false>(a, m, b, n, mode, out, ld_out, workspace, device, s);
+  }
+  return mode == AIDET_MODE_IOF ? launch_matrix<QuadKind, true>(a, m, b, n, mode, out, ld_out, workspace, device, s)
+                                : launch_matrix<QuadKind, false>(a, m, b, n, mode, out, ld_out, workspace, device, s);
+}
+
+int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out, int device,
+                           void* stream) {
+  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_aligned_f32: fmt must be 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_aligned_f32: bad mode %d", mode);
+  AIDET_REQUIRE(n >= 0, "aidet_riou_aligned_f32: negative size");
+  if (n == 0) return AIDET_OK;
+  AIDET_REQUIRE(a && b && out, "aidet_riou_aligned_f32: null pointer");
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (fmt == 5) riou_aligned_kernel<RectKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
+  else riou_aligned_kernel<QuadKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
+  count_launch(1);
+  AIDET_CUDA(cudaGetLastError());
+  return AIDET_OK;
+}
+
+}  // extern "C"

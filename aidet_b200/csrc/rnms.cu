@@ -1,0 +1,377 @@
+// rnms.cu -- batched (image x class) NMS for oriented and axis-aligned boxes on sm_100a.
+//
+// Replaces (reference):
+//   mmdet/ops/nms/src/nms_kernel.cu:24-68   64x64 bitmask tiles (lower triangle computed too)
+//   mmdet/ops/nms/src/nms_kernel.cu:71-139  device sort, D2H copy of the whole mask, serial host
+//                                           scan, H2D of keeps, cudaMalloc/Free per call
+//   mmdet/core/post_processing/rbbox_nms.py:29-49,83-106  Python loop over classes
+// with ONE device-side pass over all groups, no host round trip:
+//   1. keys    (group << 32 | ~orderable(score)), stable radix sort (CUB, the only library call)
+//              => order: group asc, score desc, original index asc on ties
+//   2. gather  sorted boxes -> prepared records (geom.cuh) + group [start,end)
+//   3. mask    upper-triangle suppression bitmask, 32-bit half-words = __ballot_sync of
+//              "IoU > thr" over 32 column boxes held in registers, row boxes staged by TMA
+//   4. scan    one warp per group walks the rows in score order (greedy), entirely on device
+//   5. compact kept flags -> ascending original indices (nms_kernel.cu:135-138 semantics)
+// Bound: step 3, FP32 issue (same pair arithmetic as riou.cu); steps 1,2,4,5 are latency.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+namespace aidet {
+
+// ------------------------------------------------------------------ box kinds
+struct NmsRect {
+  using Row = RectRow; using Col = RectCol;
+  static constexpr int FMT = 5;
+  __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { rect_prepare(p, r, c); }
+  __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return rect_overlap(a, b, MODE_IOU); }
+};
+struct NmsQuad {
+  using Row = QuadRow; using Col = QuadCol;
+  static constexpr int FMT = 8;
+  __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { quad_prepare(p, r, c); }
+  __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return quad_overlap(a, b, MODE_IOU); }
+};
+struct NmsHbb {
+  using Row = HbbBox; using Col = HbbBox;
+  static constexpr int FMT = 4;
+  __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) {
+    HbbBox b{p[0], p[1], p[2], p[3]};
+    *r = b; *c = b;
+  }
+  __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float one) {
+    return hbb_overlap(a, b, one, MODE_IOU);
+  }
+};
+
+// ------------------------------------------------------------------ 1. keys
+__device__ __forceinline__ uint32_t orderable(float f) {      // ascending uint <=> ascending float
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) nms_keys_kernel(const float* __restrict__ scores, const int* __restrict__ groups,
+                                                       int n, uint64_t* keys, int* idx, uint8_t* flags, int* gbounds,
+                                                       int n_groups) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * n_groups) gbounds[i] = 0;          // [start | end) of every group, empty by default
+  if (i >= n) return;
+  uint32_t g = groups ? (uint32_t)groups[i] : 0u;
+  keys[i] = ((uint64_t)g << 32) | (uint64_t)(~orderable(scores[i]));
+  idx[i] = i;
+  flags[i] = 0;
+}
+
+// ------------------------------------------------------------------ 2. gather
+template <class O>
+__global__ void __launch_bounds__(256) nms_gather_kernel(const float* __restrict__ boxes, const uint64_t* __restrict__ keys,
+                                                         const int* __restrict__ order, int n, float one,
+                                                         typename O::Row* rows, typename O::Col* cols, int* gstart,
+                                                         int* gend, int n_groups) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int i = order[p];
+  float b[O::FMT];
+#pragma unroll
+  for (int k = 0; k < O::FMT; k++) b[k] = boxes[(size_t)i * O::FMT + k];
+  typename O::Row r; typename O::Col c;
+  O::prepare(b, one, &r, &c);
+  rows[p] = r;
+  if constexpr (!std::is_same<typename O::Row, typename O::Col>::value) cols[p] = c;
+  int g = (int)(keys[p] >> 32);
+  if (g >= 0 && g < n_groups) {
+    if (p == 0 || (int)(keys[p - 1] >> 32) != g) gstart[g] = p;
+    if (p == n - 1 || (int)(keys[p + 1] >> 32) != g) gend[g] = p + 1;
+  }
+}
+
+// tiles of 64 rows x 256 cols over the bounding rectangle of every group (tiles under the
+// diagonal are skipped by the mask kernel); prefix[g] = first tile id of group g.
+__global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __restrict__ gstart, const int* __restrict__ gend,
+                                                               int n_groups, int* prefix) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_groups; base += 1024) {
+    int g = base + threadIdx.x;
+    int v = 0;
+    if (g < n_groups) { int ng = gend[g] - gstart[g]; v = ((ng + 63) / 64) * ((ng + 255) / 256); }
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sum[threadIdx.x];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += y; }
+      warp_sum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    int incl = x + ((threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0) + carry;
+    if (g < n_groups) prefix[g] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) prefix[n_groups] = carry;
+}
+
+// ------------------------------------------------------------------ 3. mask
+constexpr int kTileRows = 64;
+constexpr int kTileCols = 256;
+
+template <class O>
+__global__ void __launch_bounds__(kTileCols)
+nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
+                const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
+                int n_groups, const float* __restrict__ thr, int n_thr, int cmp_ge, float one,
+                uint32_t* __restrict__ mask32, long long pitch32) {
+  using Row = typename O::Row; using Col = typename O::Col;
+  __shared__ __align__(128) Row stage[kTileRows];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  const int total = prefix[n_groups];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t phase = 0;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int lo = 0, hi = n_groups;                       // last g with prefix[g] <= t
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= t) lo = mid; else hi = mid; }
+    const int g = lo;
+    const int start = gstart[g], ng = gend[g] - start;
+    const int ncq = (ng + kTileCols - 1) / kTileCols;
+    const int local = t - prefix[g];
+    const int r0 = (local / ncq) * kTileRows, cq0 = (local % ncq) * kTileCols;
+    if (cq0 + kTileCols <= r0) continue;             // tile entirely left of the diagonal word (CTA-uniform)
+    const int nr = min(kTileRows, ng - r0);
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)(nr * (int)sizeof(Row));
+      mbar_expect_tx(&bar, bytes);
+      tma_load_1d(stage, rows + start + r0, bytes, &bar);
+    }
+    const float th = thr[n_thr == 1 ? 0 : g];
+    const int c0 = cq0 + warp * 32;
+    const bool need = (c0 >= r0) && (c0 < ng);       // warp-uniform
+    const int j = c0 + lane;
+    const bool live = j < ng;
+    Col me;
+    if (need) me = cols[start + (live ? j : ng - 1)];
+    mbar_wait(&bar, phase); phase ^= 1;
+    if (need) {
+      uint32_t word = 0;
+      for (int rr = 0; rr < nr; ++rr) {
+        const int i = r0 + rr;
+        uint32_t b = 0;
+        if (i < c0 + 31) {                           // otherwise no column of this strip follows row i
+          Row s = stage[rr];
+          float ovr = O::overlap(s, me, one);
+          bool hit = cmp_ge ? (ovr >= th) : (ovr > th);
+          b = __ballot_sync(0xffffffffu, hit && live && j > i);
+        }
+        if (lane == (rr & 31)) word = b;
+        if ((rr & 31) == 31 || rr == nr - 1) {
+          int row = r0 + (rr & ~31) + lane;
+          if (lane <= (rr & 31)) mask32[(long long)(start + row) * pitch32 + (c0 >> 5)] = word;
+          word = 0;
+        }
+      }
+    }
+    __syncthreads();                                 // stage is free again
+  }
+}
+
+// ------------------------------------------------------------------ 4. scan
+// One warp per group.  `removed` (one bit per sorted position of the group) lives in shared
+// memory as 32-bit half-words.  Per 32-row block: the diagonal half-words are brought to
+// every lane with shuffles, the greedy chain runs redundantly in all lanes (no divergence),
+// then the mask rows of the kept boxes are OR-ed into the later half-words.
+__global__ void __launch_bounds__(32) nms_scan_kernel(const uint32_t* __restrict__ mask32, long long pitch32,
+                                                      const int* __restrict__ gstart, const int* __restrict__ gend,
+                                                      const int* __restrict__ order, uint8_t* __restrict__ flags) {
+  extern __shared__ uint32_t removed[];
+  const int g = blockIdx.x, lane = threadIdx.x;
+  const int start = gstart[g], ng = gend[g] - start;
+  if (ng <= 0) return;
+  const int nhw = (ng + 31) >> 5;
+  for (int h = lane; h < nhw; h += 32) removed[h] = 0;
+  __syncwarp();
+  for (int b = 0; b < nhw; ++b) {
+    const int row = b * 32 + lane;
+    const bool valid = row < ng;
+    const uint32_t* mrow = mask32 + (long long)(start + (valid ? row : 0)) * pitch32;
+    uint32_t d = valid ? mrow[b] : 0u;
+    uint32_t cur = removed[b];
+    if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);     // positions past the group end
+    uint32_t keep = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      uint32_t dk = __shfl_sync(0xffffffffu, d, k);
+      if (!(cur & (1u << k))) { keep |= 1u << k; cur |= dk; }
+    }
+    if ((keep >> lane) & 1u) flags[order[start + row]] = 1;
+    // OR the rows of the kept boxes into the half-words after b (4 rows in flight per step)
+    uint32_t todo = keep;
+    while (todo) {
+      int k0 = __ffs(todo) - 1; todo &= todo - 1;
+      int k1 = todo ? __ffs(todo) - 1 : -1; if (todo) todo &= todo - 1;
+      int k2 = todo ? __ffs(todo) - 1 : -1; if (todo) todo &= todo - 1;
+      int k3 = todo ? __ffs(todo) - 1 : -1; if (todo) todo &= todo - 1;
+      const uint32_t* m0 = mask32 + (long long)(start + b * 32 + k0) * pitch32;
+      const uint32_t* m1 = mask32 + (long long)(start + b * 32 + (k1 < 0 ? k0 : k1)) * pitch32;
+      const uint32_t* m2 = mask32 + (long long)(start + b * 32 + (k2 < 0 ? k0 : k2)) * pitch32;
+      const uint32_t* m3 = mask32 + (long long)(start + b * 32 + (k3 < 0 ? k0 : k3)) * pitch32;
+      for (int h = b + 1 + lane; h < nhw; h += 32) removed[h] |= (m0[h] | m1[h]) | (m2[h] | m3[h]);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ 5. compact
+__global__ void __launch_bounds__(1024) nms_compact_kernel(const uint8_t* __restrict__ flags, int n,
+                                                           long long* __restrict__ keep_out, int* __restrict__ n_keep) {
+  __shared__ int warp_sum[32];
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) cnt += flags[i];
+  int x = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+  if ((threadIdx.x & 31) == 31) warp_sum[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = warp_sum[threadIdx.x];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, d); if (threadIdx.x >= d) w += y; }
+    warp_sum[threadIdx.x] = w;
+  }
+  __syncthreads();
+  int off = x - cnt + ((threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0);
+  for (int i = lo; i < hi; ++i) if (flags[i]) keep_out[off++] = i;
+  if (threadIdx.x == 1023) *n_keep = off;
+}
+
+// ------------------------------------------------------------------ host side
+struct NmsLayout {
+  size_t keys_in, keys_out, idx_in, order, rows, cols, gbounds, prefix, flags, mask, cub, total;
+  long long pitch32;
+  size_t cub_bytes;
+};
+
+static int group_bits(int n_groups) { int b = 0; while ((1LL << b) < (long long)n_groups) ++b; return b; }
+
+static NmsLayout nms_layout(int n, int n_groups, int fmt, size_t cub_bytes) {
+  NmsLayout L;
+  size_t rec = (fmt == 8) ? 64 : (fmt == 5 ? 32 : 16);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 128); return o; };
+  L.keys_in = take((size_t)n * 8); L.keys_out = take((size_t)n * 8);
+  L.idx_in = take((size_t)n * 4); L.order = take((size_t)n * 4);
+  L.rows = take((size_t)n * rec); L.cols = take(fmt == 4 ? 0 : (size_t)n * rec);
+  L.gbounds = take((size_t)n_groups * 8); L.prefix = take((size_t)(n_groups + 1) * 4);
+  L.flags = take((size_t)n);
+  L.pitch32 = 2LL * ((n + 63) / 64);
+  L.mask = take((size_t)n * (size_t)L.pitch32 * 4);
+  L.cub_bytes = cub_bytes; L.cub = take(cub_bytes);
+  L.total = off + 128;
+  return L;
+}
+
+static int cub_temp_bytes(int n, int end_bit, size_t* bytes) {
+  *bytes = 0;
+  AIDET_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                             (const int*)nullptr, (int*)nullptr, n, 0, end_bit, (cudaStream_t)0));
+  return AIDET_OK;
+}
+
+template <class O>
+static int run_nms(const float* boxes, const float* scores, const int* groups, int n, const float* thr, int n_thr,
+                   int n_groups, int cmp, float one, long long* keep_out, int* n_keep, char* ws, const NmsLayout& L,
+                   int device, cudaStream_t s) {
+  using Row = typename O::Row; using Col = typename O::Col;
+  uint64_t* keys_in = (uint64_t*)(ws + L.keys_in); uint64_t* keys_out = (uint64_t*)(ws + L.keys_out);
+  int* idx_in = (int*)(ws + L.idx_in); int* order = (int*)(ws + L.order);
+  Row* rows = (Row*)(ws + L.rows);
+  Col* cols = std::is_same<Row, Col>::value ? (Col*)rows : (Col*)(ws + L.cols);
+  int* gstart = (int*)(ws + L.gbounds); int* gend = gstart + n_groups;
+  int* prefix = (int*)(ws + L.prefix);
+  uint8_t* flags = (uint8_t*)(ws + L.flags);
+  uint32_t* mask32 = (uint32_t*)(ws + L.mask);
+
+  const int nb = ceil_div(max(n, 2 * n_groups), 256);
+  nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
+  size_t cub_bytes = L.cub_bytes;
+  AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
+                                             32 + group_bits(n_groups), s));
+  nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
+  nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, prefix);
+  {
+    ProfScope prof(PROF_NMS_MASK, s);
+    const int sms = sm_count(device);
+    // upper bound of the tile count: every group padded to full tiles
+    long long max_tiles = (long long)(ceil_div(n, kTileRows) + n_groups) * (ceil_div(n, kTileCols) + 1);
+    int grid = (int)min((long long)sms * 8, max(max_tiles, 1LL));
+    nms_mask_kernel<O><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr,
+                                                  cmp == AIDET_CMP_GE ? 1 : 0, one, mask32, L.pitch32);
+  }
+  size_t scan_smem = (size_t)ceil_div(n, 32) * 4 + 16;
+  if (scan_smem > 48 * 1024) {
+    if (scan_smem > 227 * 1024) { set_error("nms: %d boxes exceed the single-group scan capacity", n); return AIDET_EINVAL; }
+    AIDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+  }
+  nms_scan_kernel<<<n_groups, 32, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags);
+  nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
+  count_launch(6);        // + the CUB sort passes, which are library kernels and not counted
+  AIDET_CUDA(cudaGetLastError());
+  return AIDET_OK;
+}
+
+}  // namespace aidet
+
+using namespace aidet;
+
+extern "C" {
+
+size_t aidet_nms_workspace_bytes(int n, int n_groups, int fmt) {
+  if (n <= 0) return 256;
+  if (n_groups < 1) n_groups = 1;
+  size_t cub_bytes = 0;
+  if (cub_temp_bytes(n, 64, &cub_bytes) != AIDET_OK) return 0;
+  return nms_layout(n, n_groups, fmt, cub_bytes).total;
+}
+
+int aidet_nms_batched_f32(const float* boxes, int fmt, const float* scores, const int* group_ids, int n,
+                          const float* thr, int n_thr, int n_groups, int cmp, int plus_one, long long* keep_out,
+                          int* n_keep, void* workspace, size_t ws_bytes, int device, void* stream) {
+  AIDET_REQUIRE(fmt == 4 || fmt == 5 || fmt == 8, "aidet_nms_batched_f32: fmt must be 4, 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(n >= 0 && n_groups >= 1, "aidet_nms_batched_f32: bad sizes n=%d n_groups=%d", n, n_groups);
+  AIDET_REQUIRE(n_thr == 1 || n_thr == n_groups, "aidet_nms_batched_f32: n_thr must be 1 or n_groups");
+  AIDET_REQUIRE(cmp == AIDET_CMP_GT || cmp == AIDET_CMP_GE, "aidet_nms_batched_f32: bad cmp %d", cmp);
+  AIDET_REQUIRE(n_keep && thr, "aidet_nms_batched_f32: null pointer");
+  AIDET_REQUIRE(group_ids || n_groups == 1, "aidet_nms_batched_f32: group_ids required when n_groups > 1");
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) { AIDET_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int), s)); return AIDET_OK; }
+  AIDET_REQUIRE(boxes && scores && keep_out && workspace, "aidet_nms_batched_f32: null pointer");
+  AIDET_REQUIRE(((uintptr_t)workspace & 127) == 0, "aidet_nms_batched_f32: workspace must be 128 B aligned");
+  size_t cub_bytes = 0;
+  if (int rc = cub_temp_bytes(n, 64, &cub_bytes)) return rc;
+  NmsLayout L = nms_layout(n, n_groups, fmt, cub_bytes);
+  if (ws_bytes < L.total) {
+    set_error("aidet_nms_batched_f32: workspace %zu < %zu", ws_bytes, L.total);
+    return AIDET_EWORKSPACE;
+  }
+  char* ws = (char*)workspace;
+  const float one = plus_one ? 1.0f : 0.0f;
+  if (fmt == 5) return run_nms<NmsRect>(boxes, scores, group_ids, n, thr, n_thr, n_groups, cmp, one, keep_out, n_keep, ws, L, device, s);
+  if (fmt == 8) return run_nms<NmsQuad>(boxes, scores, group_ids, n, thr, n_thr, n_groups, cmp, one, keep_out, n_keep, ws, L, device, s);
+  return run_nms<NmsHbb>(boxes, scores, group_ids, n, thr, n_thr, n_groups, cmp, one, keep_out, n_keep, ws, L, device, s);
+}
+
+}  // extern "C"

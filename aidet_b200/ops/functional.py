@@ -1,0 +1,168 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point of include/aidet_b200.h).
+
+Inputs are CUDA float32 tensors; nothing here touches the CPU or the oracle.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+
+def _f32c(t, cols, name):
+    L.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.dim() != 2 or t.size(1) != cols:
+        raise ValueError("%s must have shape (n, %d), got %s" % (name, cols, tuple(t.shape)))
+    return t
+
+
+def riou_matrix(a, b, mode="iou", out=None):
+    """(m,fmt) x (n,fmt) -> (m,n) float32 overlap matrix, fmt 5 (cx,cy,w,h,theta) or 8 (x1..y4)."""
+    assert mode in ("iou", "iof")
+    fmt = a.size(-1)
+    a, b = _f32c(a, fmt, "a"), _f32c(b, fmt, "b")
+    if a.device != b.device:
+        raise ValueError("a and b must be on the same device")
+    m, n = a.size(0), b.size(0)
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    if m == 0 or n == 0:
+        return out
+    assert out.is_cuda and out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (m, n)
+    dev = a.device.index
+    lib = L.lib()
+    ws_bytes = lib.aidet_riou_workspace_bytes(m, n, fmt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(dev):
+        L.check(lib.aidet_riou_matrix_f32(L.dptr(a), m, L.dptr(b), n, fmt, L.MODE_IOF if mode == "iof" else L.MODE_IOU,
+                                          L.dptr(out), out.stride(0), L.dptr(ws), ws_bytes, dev, L.stream_ptr(dev)),
+                "aidet_riou_matrix_f32")
+    return out
+
+
+def riou_aligned(a, b, mode="iou"):
+    assert mode in ("iou", "iof")
+    fmt = a.size(-1)
+    a, b = _f32c(a, fmt, "a"), _f32c(b, fmt, "b")
+    if a.shape != b.shape:
+        raise ValueError("aligned overlaps need equal shapes, got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    n = a.size(0)
+    out = torch.empty((n,), dtype=torch.float32, device=a.device)
+    if n == 0:
+        return out
+    dev = a.device.index
+    with torch.cuda.device(dev):
+        L.check(L.lib().aidet_riou_aligned_f32(L.dptr(a), L.dptr(b), n, fmt,
+                                               L.MODE_IOF if mode == "iof" else L.MODE_IOU, L.dptr(out), dev,
+                                               L.stream_ptr(dev)), "aidet_riou_aligned_f32")
+    return out
+
+
+def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False):
+    """Batched greedy NMS.  boxes (n,4|5|8), scores (n,), group_ids (n,) int or None.
+
+    iou_thr: float, or a (n_groups,) tensor / sequence of per-group thresholds.
+    Returns keep (k,) int64, ascending original index.
+    """
+    fmt = boxes.size(-1)
+    boxes = _f32c(boxes, fmt, "boxes")
+    L.require_cuda(scores, "scores")
+    n = boxes.size(0)
+    scores = scores.reshape(-1).float().contiguous()
+    if scores.numel() != n:
+        raise ValueError("scores must have one entry per box")
+    device = boxes.device
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.long, device=device)
+    if group_ids is None:
+        n_groups = 1
+        gids = None
+    else:
+        gids = group_ids.reshape(-1).to(device=device, dtype=torch.int32).contiguous()
+        if gids.numel() != n:
+            raise ValueError("group_ids must have one entry per box")
+        if n_groups is None:
+            n_groups = int(gids.max().item()) + 1
+    if isinstance(iou_thr, torch.Tensor):
+        thr = iou_thr.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+    elif isinstance(iou_thr, (list, tuple)):
+        thr = torch.tensor(list(iou_thr), dtype=torch.float32, device=device)
+    else:
+        thr = torch.full((1,), float(iou_thr), dtype=torch.float32, device=device)
+    if thr.numel() not in (1, n_groups):
+        raise ValueError("iou_thr must be a scalar or have n_groups=%d entries" % n_groups)
+    dev = device.index
+    lib = L.lib()
+    keep = torch.empty((n,), dtype=torch.long, device=device)
+    n_keep = torch.empty((1,), dtype=torch.int32, device=device)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.aidet_nms_workspace_bytes(n, n_groups, fmt)
+        if ws_bytes == 0:
+            L.check(-2, "aidet_nms_workspace_bytes")
+        ws = torch.empty(ws_bytes + 128, dtype=torch.uint8, device=device)
+        base = ws.data_ptr()
+        aligned = (base + 127) // 128 * 128
+        L.check(lib.aidet_nms_batched_f32(L.dptr(boxes), fmt, L.dptr(scores), L.dptr(gids), n, L.dptr(thr),
+                                          thr.numel(), n_groups, L.CMP_GE if cmp_ge else L.CMP_GT,
+                                          int(bool(plus_one)), L.dptr(keep), L.dptr(n_keep), C.c_void_p(aligned),
+                                          ws_bytes, dev, L.stream_ptr(dev)), "aidet_nms_batched_f32")
+    k = int(n_keep.item())
+    return keep[:k]
+
+
+def _level_tables(tensors):
+    n = len(tensors)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    Hs = (C.c_int * n)(*[t.size(1) for t in tensors])
+    Ws = (C.c_int * n)(*[t.size(2) for t in tensors])
+    return ptrs, Hs, Ws
+
+
+def rroi_align_forward(feats_nhwc, rois, scales, out_size, sample_num, variant, roi_level=None):
+    """feats_nhwc: list of (N,H_l,W_l,C) contiguous float32; rois (K,5|6) -> (K,ph,pw,C)."""
+    ph, pw = out_size
+    f0 = feats_nhwc[0]
+    N, C_ = f0.size(0), f0.size(3)
+    for t in feats_nhwc:
+        L.require_cuda(t, "features")
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.size(0) == N and t.size(3) == C_
+    rois = _f32c(rois, rois.size(-1), "rois")
+    K = rois.size(0)
+    out = torch.empty((K, ph, pw, C_), dtype=torch.float32, device=f0.device)
+    if K == 0:
+        return out
+    lvl = None if roi_level is None else roi_level.to(device=f0.device, dtype=torch.int32).contiguous()
+    ptrs, Hs, Ws = _level_tables(feats_nhwc)
+    sc = (C.c_float * len(scales))(*[float(s) for s in scales])
+    dev = f0.device.index
+    with torch.cuda.device(dev):
+        L.check(L.lib().aidet_rroi_align_fwd_f32(ptrs, Hs, Ws, sc, len(feats_nhwc), N, C_, L.dptr(rois), rois.size(1),
+                                                 L.dptr(lvl), K, ph, pw, int(sample_num), int(variant), L.dptr(out),
+                                                 dev, L.stream_ptr(dev)), "aidet_rroi_align_fwd_f32")
+    return out
+
+
+def rroi_align_backward(grad_out_nhwc, grad_feats_nhwc, rois, scales, sample_num, variant, roi_level=None):
+    """Accumulates into the (pre-zeroed) grad_feats_nhwc list; grad_out (K,ph,pw,C) contiguous."""
+    g0 = grad_feats_nhwc[0]
+    N, C_ = g0.size(0), g0.size(3)
+    L.require_cuda(grad_out_nhwc, "grad_output")
+    assert grad_out_nhwc.dtype == torch.float32 and grad_out_nhwc.is_contiguous()
+    K, ph, pw, C2 = grad_out_nhwc.shape
+    assert C2 == C_
+    for t in grad_feats_nhwc:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.size(0) == N and t.size(3) == C_
+    if K == 0:
+        return
+    rois = _f32c(rois, rois.size(-1), "rois")
+    lvl = None if roi_level is None else roi_level.to(device=g0.device, dtype=torch.int32).contiguous()
+    ptrs, Hs, Ws = _level_tables(grad_feats_nhwc)
+    sc = (C.c_float * len(scales))(*[float(s) for s in scales])
+    dev = g0.device.index
+    with torch.cuda.device(dev):
+        L.check(L.lib().aidet_rroi_align_bwd_f32(L.dptr(grad_out_nhwc), ptrs, Hs, Ws, sc, len(grad_feats_nhwc), N, C_,
+                                                 L.dptr(rois), rois.size(1), L.dptr(lvl), K, ph, pw, int(sample_num),
+                                                 int(variant), dev, L.stream_ptr(dev)), "aidet_rroi_align_bwd_f32")

@@ -1,0 +1,116 @@
+"""Synthetic DOTA-shaped inputs shared by tests/ and bench.py.
+
+All generators are seeded `torch.Generator(device='cpu')` streams and return float32 CPU
+tensors; callers move them to the GPU.  Nothing here is part of the compute path.
+"""
+import math
+
+import torch
+
+
+def _gen(seed):
+    g = torch.Generator(device='cpu')
+    g.manual_seed(int(seed))
+    return g
+
+
+def _uniform(g, n, lo, hi):
+    return torch.rand(n, generator=g, dtype=torch.float64) * (hi - lo) + lo
+
+
+def dota_boxes(n, side=1024, seed=0, dense=False):
+    """(n,5) theta-OBBs (cx,cy,w,h,theta[rad]) and (n,) scores.
+
+    DOTA-shaped: 70 % of the centres around n/40 cluster centres (sigma 24 px), 30 % uniform;
+    long side exp(U(ln 8, ln 256)), aspect U(1,6), theta U(-pi/2, pi/2), scores U(0,1).
+    dense=True: every centre inside one 16 px disc, long side exp(U(ln 96, ln 256)), aspect
+    U(1,1.5) -- every pair truly intersects, so no early-out can fire (roofline runs).
+    """
+    g = _gen(seed)
+    if dense:
+        r = 16.0 * torch.sqrt(_uniform(g, n, 0, 1))
+        ph = _uniform(g, n, 0, 2 * math.pi)
+        cx = side / 2 + r * torch.cos(ph)
+        cy = side / 2 + r * torch.sin(ph)
+        long_side = torch.exp(_uniform(g, n, math.log(96), math.log(256)))
+        aspect = _uniform(g, n, 1, 1.5)
+    else:
+        n_clu = max(n // 40, 1)
+        centres = _uniform(g, 2 * n_clu, 0, side).view(n_clu, 2)
+        which = torch.randint(0, n_clu, (n,), generator=g)
+        clustered = _uniform(g, n, 0, 1) < 0.7
+        jitter = torch.randn(n, 2, generator=g, dtype=torch.float64) * 24.0
+        uni = _uniform(g, 2 * n, 0, side).view(n, 2)
+        c = torch.where(clustered[:, None], centres[which] + jitter, uni)
+        cx, cy = c[:, 0], c[:, 1]
+        long_side = torch.exp(_uniform(g, n, math.log(8), math.log(256)))
+        aspect = _uniform(g, n, 1, 6)
+    swap = _uniform(g, n, 0, 1) < 0.5
+    w = torch.where(swap, long_side, long_side / aspect)
+    h = torch.where(swap, long_side / aspect, long_side)
+    theta = _uniform(g, n, -math.pi / 2, math.pi / 2)
+    scores = _uniform(g, n, 0, 1)
+    boxes = torch.stack([cx, cy, w, h, theta], dim=1).float()
+    return boxes, scores.float()
+
+
+def thetaobb2pointobb(boxes):
+    """(n,5) -> (n,8) in cv2.boxPoints order (mmdet/core/rbbox/transforms.py:45-55), float64 math."""
+    b = boxes.double()
+    cx, cy, w, h, th = b.unbind(1)
+    c, s = torch.cos(th) * 0.5, torch.sin(th) * 0.5
+    x0 = cx - s * h - c * w
+    y0 = cy + c * h - s * w
+    x1 = cx + s * h - c * w
+    y1 = cy - c * h - s * w
+    return torch.stack([x0, y0, x1, y1, 2 * cx - x0, 2 * cy - y0, 2 * cx - x1, 2 * cy - y1], dim=1).float()
+
+
+def multiclass_dets(n=2000, num_classes=15, side=1024, seed=2, dense=False, dim=5):
+    """Config C2: (n, (C+1)*5) class-specific theta-OBBs and (n, C+1) softmax scores.
+
+    Every class regresses a jittered copy of the proposal; scores = softmax(3 N(0,1)) over
+    C+1 columns (column 0 = background), to be filtered at > 0.05 (rbbox_nms.py:30).
+    """
+    g = _gen(seed)
+    base, _ = dota_boxes(n, side=side, seed=seed + 1000, dense=dense)
+    jit = torch.randn(n, num_classes + 1, 5, generator=g) * torch.tensor([2.0, 2.0, 1.0, 1.0, 0.02])
+    boxes = base[:, None, :] + jit
+    boxes[..., 2:4] = boxes[..., 2:4].clamp(min=2.0)
+    scores = torch.softmax(3.0 * torch.randn(n, num_classes + 1, generator=g), dim=1)
+    if dim == 8:
+        boxes = thetaobb2pointobb(boxes.view(-1, 5)).view(n, num_classes + 1, 8)
+    return boxes.reshape(n, -1).contiguous(), scores.contiguous()
+
+
+def fpn_features(batch=8, channels=256, tile=1024, strides=(4, 8, 16, 32), seed=3):
+    """Config C3 features: list of NHWC float32 randn maps (N, tile/s, tile/s, C)."""
+    g = _gen(seed)
+    return [torch.randn(batch, tile // s, tile // s, channels, generator=g) for s in strides]
+
+
+def rotated_rois(rois_per_img=512, batch=8, tile=1024, seed=3, num_levels=4, finest_scale=56):
+    """Config C3 RoIs: (K,6) [b,cx,cy,w,h,theta] + level ids by the rule of
+    mmdet/models/roi_extractors/single_level.py:69-73 (scale = sqrt(w*h))."""
+    g = _gen(seed + 77)
+    k = rois_per_img * batch
+    side = torch.exp(_uniform(g, k, math.log(16), math.log(512)))
+    aspect = _uniform(g, k, 1, 4)
+    swap = _uniform(g, k, 0, 1) < 0.5
+    w = torch.where(swap, side, side / aspect)
+    h = torch.where(swap, side / aspect, side)
+    theta = _uniform(g, k, -math.pi / 2, math.pi / 2)
+    cx = _uniform(g, k, 0, tile)
+    cy = _uniform(g, k, 0, tile)
+    b = torch.arange(batch, dtype=torch.float64).repeat_interleave(rois_per_img)
+    rois = torch.stack([b, cx, cy, w, h, theta], dim=1).float()
+    scale = torch.sqrt(rois[:, 3] * rois[:, 4])
+    lvl = torch.floor(torch.log2(scale / finest_scale + 1e-6)).clamp(min=0, max=num_levels - 1).int()
+    return rois, lvl
+
+
+def scene_tiles(scene=4000, tile=1024, overlap=200):
+    """Config C5 tile origins: stride tile-overlap, last one clamped to scene-tile."""
+    step = tile - overlap
+    xs = list(range(0, scene - tile, step)) + [scene - tile]
+    return [(x, y) for y in xs for x in xs]

@@ -1,0 +1,113 @@
+/*
+ * aidet_b200.h -- C ABI of libaidet_b200.so: B200 (sm_100a) oriented-bounding-box ops
+ * behind AIDet's mmdet.ops interface.
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless
+ *     the name ends in _host; the caller owns every buffer (including workspaces)
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and the
+ *     call returns without synchronising unless stated
+ *   - returns 0 on success, a negative AIDET_E* code otherwise; the message is
+ *     available from aidet_last_error() (thread local).  Nothing throws, exits or
+ *     prints (the reference's pybind layer raises from AT_CHECK/AT_ASSERTM --
+ *     mmdet/ops/nms/src/nms_cuda.cpp:4,9, mmdet/ops/roi_align/src/roi_align_cuda.cpp:37-42
+ *     -- and its v1 RoIAlign printf()s / exit(-1)s, roi_align_cuda.cpp:56-59,
+ *     roi_align_kernel.cu:269-272; the Python shim turns codes into RuntimeError)
+ *   - box formats: 4 = HBB (x1,y1,x2,y2), 5 = theta-OBB (cx,cy,w,h,theta[rad]),
+ *     8 = point-OBB (x1,y1,...,x4,y4)   (mmdet/core/rbbox/transforms.py:45-55)
+ *
+ * The reference-side binding for each function is shown in INTEGRATION.md.
+ */
+#ifndef AIDET_B200_H_
+#define AIDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIDET_OK 0
+#define AIDET_EINVAL (-1)   /* bad argument */
+#define AIDET_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define AIDET_EWORKSPACE (-3) /* workspace too small */
+
+#define AIDET_MODE_IOU 0
+#define AIDET_MODE_IOF 1
+#define AIDET_CMP_GT 0      /* suppress when ovr >  thr : mmdet/ops/nms/src/nms_kernel.cu:61 */
+#define AIDET_CMP_GE 1      /* suppress when ovr >= thr : mmdet/ops/nms/src/nms_cpu.cpp:56   */
+
+/* ---- library ------------------------------------------------------------ */
+const char* aidet_last_error(void);
+int aidet_version(void);                       /* 100 * major + minor */
+/* Device-side timing of the dominant kernel of each op (CUDA events recorded on
+ * the caller's stream around that kernel only).  enable != 0 starts collecting. */
+int aidet_prof_enable(int enable);
+/* kind: 0 = riou matrix kernel, 1 = rnms mask kernel, 2 = rroi fwd kernel,
+ * 3 = rroi bwd kernel.  Synchronises the recorded events, returns accumulated
+ * milliseconds and launch count since the last reset. */
+int aidet_prof_read(int kind, double* ms_total, long long* launches, int reset);
+/* Total number of kernel launches issued by this library since load (all ops). */
+long long aidet_launch_count(void);
+/* FP32 FFMA micro-benchmark (roofline denominator for the ALU-bound kernels):
+ * runs `iters` dependent-free FFMA chains on every SM, returns TFLOP/s. */
+int aidet_ffma_peak(int device, int iters, double* tflops_out, void* stream);
+
+/* ---- rotated IoU ---------------------------------------------------------
+ * Replaces: the polygon IoU AIDet reaches through wwtool (mmdet/datasets/dota.py:23,336)
+ * and the (m,n) overlap API of mmdet/core/bbox/geometry.py:4-88 for rotated boxes.
+ * a: (m,fmt) row-major, b: (n,fmt); out: m rows of n floats, row stride ld_out
+ * (elements).  workspace >= aidet_riou_workspace_bytes(m,n,fmt), 16 B aligned. */
+size_t aidet_riou_workspace_bytes(int m, int n, int fmt);
+int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt, int mode,
+                          float* out, long long ld_out, void* workspace, size_t ws_bytes,
+                          int device, void* stream);
+/* element-wise pairs (is_aligned=True, geometry.py:57-71): out[i] = ovr(a[i], b[i]) */
+int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out,
+                           int device, void* stream);
+
+/* ---- batched NMS (rotated and axis-aligned) -------------------------------
+ * Replaces: nms_cuda.nms (mmdet/ops/nms/src/nms_kernel.cu:71-139: sort, 64x64 bitmask
+ * tiles, D2H mask copy, host scan) and the per-class Python loops of
+ * mmdet/core/post_processing/rbbox_nms.py:29-49,83-106 with one device-side pass:
+ * sort by (group, -score, index) -> upper-triangle suppression bitmask (64-bit words)
+ * -> on-device greedy scan per group -> compaction.
+ *   boxes (n,fmt) fmt in {4,5,8}; scores (n); group_ids (n) in [0,n_groups) or NULL;
+ *   thr: n_thr == 1 (shared) or n_thr == n_groups (per group, dota.py:324);
+ *   plus_one: legacy +1 pixel convention, fmt 4 only (nms_kernel.cu:17-21);
+ *   keep_out (n) int64, ascending ORIGINAL index (nms_kernel.cu:135-138);
+ *   n_keep: device int32 scalar.                                              */
+size_t aidet_nms_workspace_bytes(int n, int n_groups, int fmt);
+int aidet_nms_batched_f32(const float* boxes, int fmt, const float* scores, const int* group_ids,
+                          int n, const float* thr, int n_thr, int n_groups, int cmp, int plus_one,
+                          long long* keep_out, int* n_keep, void* workspace, size_t ws_bytes,
+                          int device, void* stream);
+
+/* ---- rotated / axis-aligned RoIAlign, multi-level, NHWC -------------------
+ * Replaces: roi_align_cuda.forward_v1/v2, backward_v1/v2
+ * (mmdet/ops/roi_align/src/roi_align_kernel.cu:64-141,187-283, roi_align_kernel_v2.cu:62-348)
+ * and the per-level loop of mmdet/models/roi_extractors/single_level.py:89-107.
+ *   feat[l]: (N, H[l], W[l], C) float32 channels-last, l < n_levels (HOST array of
+ *            DEVICE pointers, likewise H, W, spatial_scale are host arrays)
+ *   rois: (K, roi_fmt) roi_fmt 5 = [b,x1,y1,x2,y2], 6 = [b,cx,cy,w,h,theta]
+ *   roi_level: (K) int32 level of each RoI, or NULL when n_levels == 1
+ *   variant: 0 = v1 legacy (+1, roi_align_kernel.cu:79-86), 1 = v2 aligned=false,
+ *            2 = v2 aligned=true (roi_align_kernel_v2.cu:79-90)
+ *   out / grad_out: (K, ph, pw, C) float32
+ *   backward accumulates into grad_feat[l] (caller zero-fills, as roi_align.py:63-64) */
+int aidet_rroi_align_fwd_f32(const float* const* feat_host, const int* H_host, const int* W_host,
+                             const float* scale_host, int n_levels, int N, int C,
+                             const float* rois, int roi_fmt, const int* roi_level, int K,
+                             int ph, int pw, int sample_num, int variant,
+                             float* out, int device, void* stream);
+int aidet_rroi_align_bwd_f32(const float* grad_out, float* const* grad_feat_host, const int* H_host,
+                             const int* W_host, const float* scale_host, int n_levels, int N, int C,
+                             const float* rois, int roi_fmt, const int* roi_level, int K,
+                             int ph, int pw, int sample_num, int variant,
+                             int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIDET_B200_H_ */

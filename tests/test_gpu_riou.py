@@ -1,0 +1,122 @@
+"""GPU parity: rotated IoU (C ABI -> aidet_b200.core.rbbox_overlaps) vs the float64 oracle.
+
+Tolerance (BASELINE.json north_star): IoU within 1e-5 absolute.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from aidet_b200 import synth
+from aidet_b200.core import rbbox_overlaps
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _check(a, b, cuda, mode="iou", tol=TOL):
+    got = rbbox_overlaps(a.to(cuda), b.to(cuda), mode=mode).cpu().numpy().astype(np.float64)
+    ref = O.riou_matrix(a.numpy(), b.numpy(), mode=mode)
+    err = np.abs(got - ref)
+    assert err.max() <= tol, "max err %.3g at %s" % (err.max(), np.unravel_index(err.argmax(), err.shape))
+    return got, ref
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_c1_matrix_2000(cuda, dense):
+    """Config C1: 2000 x 2000 theta-OBB matrix (seeds 0 / 1), DOTA-shaped and dense variants."""
+    a, _ = synth.dota_boxes(2000, seed=0, dense=dense)
+    b, _ = synth.dota_boxes(2000, seed=1, dense=dense)
+    got, ref = _check(a, b, cuda)
+    if dense:
+        assert (ref > 0).all()
+
+
+def test_iof_mode(cuda):
+    a, _ = synth.dota_boxes(700, seed=5)
+    b, _ = synth.dota_boxes(900, seed=6)
+    _check(a, b, cuda, mode="iof")
+
+
+def test_pointobb_matches_thetaobb(cuda):
+    a, _ = synth.dota_boxes(600, seed=7)
+    b, _ = synth.dota_boxes(500, seed=8)
+    a8, b8 = synth.thetaobb2pointobb(a), synth.thetaobb2pointobb(b)
+    got8, _ = _check(a8, b8, cuda)
+    got5, _ = _check(a, b, cuda)
+    assert np.abs(got8 - got5).max() <= 2e-5          # 8-point inputs are rounded to f32
+
+
+def test_general_quads(cuda):
+    """point-OBB heads regress free quadrilaterals: convex but not rectangles."""
+    g = torch.Generator().manual_seed(11)
+    a, _ = synth.dota_boxes(400, side=300, seed=9)
+    b, _ = synth.dota_boxes(400, side=300, seed=10)
+    a8 = synth.thetaobb2pointobb(a) + torch.randn(400, 8, generator=g) * 1.5
+    b8 = synth.thetaobb2pointobb(b) + torch.randn(400, 8, generator=g) * 1.5
+    # clockwise input order must give the same answer
+    b8_cw = b8.view(-1, 4, 2).flip(1).reshape(-1, 8).contiguous()
+    got, ref = _check(a8, b8, cuda, tol=2e-5)
+    got_cw, _ = _check(a8, b8_cw, cuda, tol=2e-5)
+    assert np.abs(got - got_cw).max() <= 2e-5
+
+
+def test_known_answers(cuda):
+    sq = torch.tensor([[0, 0, 2, 2, 0.0]])
+    rot = torch.tensor([[0, 0, 2, 2, math.pi / 4]])
+    v = rbbox_overlaps(sq.to(cuda), rot.to(cuda)).item()
+    assert abs(v - 0.70710678) < 1e-6                  # inter = 8(sqrt2 - 1)
+    far = torch.tensor([[100, 100, 2, 2, 0.3]])
+    assert rbbox_overlaps(sq.to(cuda), far.to(cuda)).item() == 0.0
+    box = torch.tensor([[10, 10, 4, 2, 0.3]])
+    for other in ([10, 10, 4, 2, 0.3], [10, 10, 4, 2, 0.3 + math.pi], [10, 10, 2, 4, 0.3 + math.pi / 2]):
+        v = rbbox_overlaps(box.to(cuda), torch.tensor([other], dtype=torch.float32).to(cuda)).item()
+        assert abs(v - 1.0) < 2e-6
+    # theta = 0 pair: closed-form axis-aligned IoU without +1
+    a = torch.tensor([[5, 5, 10, 10, 0.0]])
+    b = torch.tensor([[10, 5, 10, 10, 0.0]])
+    assert abs(rbbox_overlaps(a.to(cuda), b.to(cuda)).item() - 50.0 / 150.0) < 1e-6
+
+
+def test_symmetry_and_invariance(cuda):
+    a, _ = synth.dota_boxes(300, side=200, seed=12)
+    b, _ = synth.dota_boxes(300, side=200, seed=13)
+    m_ab = rbbox_overlaps(a.to(cuda), b.to(cuda))
+    m_ba = rbbox_overlaps(b.to(cuda), a.to(cuda))
+    assert (m_ab - m_ba.t()).abs().max().item() <= 2e-6
+    shift = torch.tensor([500.0, -300.0, 0, 0, 0])
+    m_sh = rbbox_overlaps((a + shift).to(cuda), (b + shift).to(cuda))
+    assert (m_ab - m_sh).abs().max().item() <= 5e-6
+
+
+def test_aligned_and_empty(cuda):
+    a, _ = synth.dota_boxes(1000, seed=14)
+    b = a.clone()
+    b[:, :2] += 3.0
+    b[:, 4] += 0.1
+    got = rbbox_overlaps(a.to(cuda), b.to(cuda), is_aligned=True).cpu().numpy()
+    ref = O.riou_aligned(a.numpy(), b.numpy())
+    assert got.shape == (1000,) and np.abs(got - ref).max() <= TOL
+    got_f = rbbox_overlaps(a.to(cuda), b.to(cuda), mode="iof", is_aligned=True).cpu().numpy()
+    assert np.abs(got_f - O.riou_aligned(a.numpy(), b.numpy(), mode="iof")).max() <= TOL
+    e = torch.zeros((0, 5), device=cuda)
+    assert tuple(rbbox_overlaps(e, a[:1].to(cuda)).shape) == (0, 1)
+    assert tuple(rbbox_overlaps(a[:1].to(cuda), e).shape) == (1, 0)
+    assert tuple(rbbox_overlaps(e, e).shape) == (0, 0)
+    assert tuple(rbbox_overlaps(e, e, is_aligned=True).shape) == (0, 1)
+
+
+def test_ragged_sizes(cuda):
+    """tile tails: sizes around the 256-column / 64-row tile edges."""
+    for m, n in [(1, 1), (63, 257), (65, 255), (130, 513), (1, 1000), (1000, 1)]:
+        a, _ = synth.dota_boxes(m, side=200, seed=20 + m)
+        b, _ = synth.dota_boxes(n, side=200, seed=40 + n)
+        _check(a, b, cuda)
+
+
+def test_cpu_tensor_raises():
+    a, _ = synth.dota_boxes(4, seed=1)
+    with pytest.raises(NotImplementedError):
+        rbbox_overlaps(a, a)
