@@ -18,10 +18,13 @@ def install_as_mmdet(force=False):
     """Expose the ops under `mmdet.ops.*` names inside an existing mmdet install (or stand-alone)."""
     import sys
     import types
+    # `ops.nms` / `ops.roi_align` the attributes are functions (as in mmdet.ops); take the modules
+    nms_pkg = sys.modules[__name__ + '.ops.nms']
+    nms_wrapper = sys.modules[__name__ + '.ops.nms.nms_wrapper']
     names = {
-        'mmdet.ops.nms': ops.nms,
-        'mmdet.ops.nms.nms_wrapper': ops.nms.nms_wrapper,
-        'mmdet.ops.roi_align': ops.roi_align,
+        'mmdet.ops.nms': nms_pkg,
+        'mmdet.ops.nms.nms_wrapper': nms_wrapper,
+        'mmdet.ops.roi_align': sys.modules[__name__ + '.ops.roi_align'],
     }
     if 'mmdet' in sys.modules and not force:
         mm_ops = sys.modules.get('mmdet.ops')
@@ -31,7 +34,7 @@ def install_as_mmdet(force=False):
             nw = sys.modules.get('mmdet.ops.nms.nms_wrapper')
             if nw is not None:
                 for k in ('nms', 'thetaobb_nms', 'pointobb_nms', 'batched_rnms'):
-                    setattr(nw, k, getattr(ops.nms.nms_wrapper, k))
+                    setattr(nw, k, getattr(nms_wrapper, k))
         mm_core = sys.modules.get('mmdet.core')
         if mm_core is not None:
             for k in core.__all__:

@@ -62,7 +62,7 @@ struct AIDET_ALIGN16 RectCol {   // the box whose frame is used ("B")
 
 // point-OBB (general simple quad), 64 B each.
 struct AIDET_ALIGN16 QuadRow {
-  float x[4], y[4];              // CCW
+  float x[4], y[4];              // CCW corner offsets about the centroid (mx,my)
   float area, rad, mx, my;       // |area|, bounding radius about (mx,my)
   float pad[4];
 };
@@ -80,23 +80,24 @@ struct AIDET_ALIGN16 HbbBox { float x1, y1, x2, y2; };
 // ------------------------------------------------- rect ^ rect (theta-OBB)
 
 // Edge integral described in the header comment, for the edge p + t d, t in [0,1].
-//   rdx, rdy : 1/dx, 1/dy of the (tiny-guarded) edge vector
-//   Ws, Hs   : copysign(W, dx), copysign(H, dy) -- orders the slab crossings so
-//              that no min/max is needed to sort them
-// The in-slab parameter range [t0,t1] is split at the x = -+W crossings into a
-// "before" piece (clamp value -Ws), an inside piece (value = x at its middle)
-// and an "after" piece (value +Ws).  All piece lengths are max(0, .) of
-// differences, so an empty range contributes exactly 0 without a branch.
-AIDET_HD float rect_edge(float px, float py, float hdx, float dy, float rdx, float rdy, float Ws, float Hs) {
+//   hdx, hdy : half of the edge vector (tiny-guarded), rdx, rdy : 1/dx, 1/dy
+//   x1st, x2nd : the slab bounds in the order this edge direction meets them
+//                (x-lo, x-hi if dx > 0, swapped otherwise); Hs = copysign(H, dy)
+// The in-slab parameter range [t0,t1] is split at the two x crossings into a "before"
+// piece (clamp value x1st), an inside piece (value = x at its middle) and an "after"
+// piece (value x2nd).  All piece lengths are max(0, .) of differences, so an empty
+// range contributes exactly 0 without a branch.
+AIDET_HD float rect_edge(float px, float py, float hdx, float hdy, float rdx, float rdy, float x1st, float x2nd,
+                         float Hs) {
   float t0 = fmaxf((-Hs - py) * rdy, 0.0f);
   float t1 = fminf((Hs - py) * rdy, 1.0f);
-  float xa = (-Ws - px) * rdx, xb = (Ws - px) * rdx;      // xa <= xb
+  float xa = (x1st - px) * rdx, xb = (x2nd - px) * rdx;      // xa <= xb
   float i0 = fmaxf(t0, xa), i1 = fminf(t1, xb);
   float tin = fmaxf(i1 - i0, 0.0f);
   float tbe = fmaxf(fminf(t1, xa) - t0, 0.0f);
   float taf = fmaxf(t1 - fmaxf(t0, xb), 0.0f);
   float xmid = fmaf(hdx, i0 + i1, px);
-  return dy * fmaf(Ws, taf - tbe, tin * xmid);
+  return hdy * fmaf(taf, x2nd, fmaf(tbe, x1st, tin * xmid));
 }
 
 AIDET_HD float guard_tiny(float d) { return (fabsf(d) > 1e-18f) ? d : 1e-18f; }
@@ -108,18 +109,26 @@ AIDET_HD float rect_inter(const RectRow& a, const RectCol& b) {
   float rx = fmaf(b.c, relx, b.s * rely), ry = fmaf(b.c, rely, -b.s * relx);
   float ux = guard_tiny(fmaf(b.c, a.ux, b.s * a.uy)), uy = guard_tiny(fmaf(b.c, a.uy, -b.s * a.ux));
   float vx = guard_tiny(fmaf(b.c, a.vx, b.s * a.vy)), vy = guard_tiny(fmaf(b.c, a.vy, -b.s * a.vx));
+  // Shift x by xref = clamp(rx): the contour integral of a constant times 1[|y|<=H] dy over
+  // a closed polygon is 0, so the result is unchanged, but every term is now of the order
+  // of the SMALLER box, which keeps the rounding error relative to the intersection.
+  float xref = fminf(fmaxf(rx, -b.W), b.W);
+  float xlo = -b.W - xref, xhi = b.W - xref;
+  rx -= xref;
   // corners p0 = r-u-v, p1 = r+u-v, p3 = r-u+v  (CCW: p0,p1,p2,p3)
   float mx = rx - ux, my = ry - uy;
   float p0x = mx - vx, p0y = my - vy;
   float p3x = mx + vx, p3y = my + vy;
   float p1x = (rx + ux) - vx, p1y = (ry + uy) - vy;
-  // edge vectors are +-2u, +-2v:  1/(2u) = 0.5/u, half of dx = u
+  // edge vectors are +-2u, +-2v:  1/(2u) = 0.5/u
   float rux = 0.5f * frcp(ux), ruy = 0.5f * frcp(uy), rvx = 0.5f * frcp(vx), rvy = 0.5f * frcp(vy);
-  float Wu = copysignf(b.W, ux), Hu = copysignf(b.H, uy), Wv = copysignf(b.W, vx), Hv = copysignf(b.H, vy);
+  float u1 = ux > 0.0f ? xlo : xhi, u2 = ux > 0.0f ? xhi : xlo;
+  float v1 = vx > 0.0f ? xlo : xhi, v2 = vx > 0.0f ? xhi : xlo;
+  float Hu = copysignf(b.H, uy), Hv = copysignf(b.H, vy);
   // edges p0->p1 (+2u), p1->p2 (+2v), p2->p3 == -(p3->p2, +2u), p3->p0 == -(p0->p3, +2v)
-  float su = rect_edge(p0x, p0y, ux, uy, rux, ruy, Wu, Hu) - rect_edge(p3x, p3y, ux, uy, rux, ruy, Wu, Hu);
-  float sv = rect_edge(p1x, p1y, vx, vy, rvx, rvy, Wv, Hv) - rect_edge(p0x, p0y, vx, vy, rvx, rvy, Wv, Hv);
-  return 2.0f * (su + sv);       // dy was passed as half the edge's dy
+  float su = rect_edge(p0x, p0y, ux, uy, rux, ruy, u1, u2, Hu) - rect_edge(p3x, p3y, ux, uy, rux, ruy, u1, u2, Hu);
+  float sv = rect_edge(p1x, p1y, vx, vy, rvx, rvy, v1, v2, Hv) - rect_edge(p0x, p0y, vx, vy, rvx, rvy, v1, v2, Hv);
+  return 2.0f * (su + sv);       // rect_edge used half of each edge's dy
 }
 
 AIDET_HD float finish_overlap(float inter, float area_a, float area_b, int mode) {
@@ -157,32 +166,43 @@ AIDET_HD float mean_pos(float f0, float f1) {
   return 0.5f * (p0 + p1) * rho;
 }
 
-// edge integral in a triangle's affine frame: Q = clamp(xi,0,1-eta) 1[0<=eta<=1]
-AIDET_HD float tri_edge(float xp, float ep, float xq, float eq) {
-  float de = eq - ep, dx = xq - xp;
+// Edge integral in a triangle's affine frame: Q = clamp(xi, 0, 1-eta) 1[0<=eta<=1], written in
+// coordinates shifted by a constant xi_ref (which leaves the closed contour integral unchanged):
+//   X = xi - xi_ref,  lo = -xi_ref,  Hi = (1 - eta) - xi_ref,  clamp(X, lo, Hi) = X - (X-Hi)+ + (lo-X)+
+// (Xp,Ep,Hp) / (Xq,Eq,Hq): X, eta, Hi at the edge's end points.
+AIDET_HD float tri_edge(float Xp, float Ep, float Hp, float Xq, float Eq, float Hq, float lo) {
+  float de = Eq - Ep, dX = Xq - Xp, dH = Hq - Hp;
   float rde = frcp(de);
-  float ta = -ep * rde, tb = (1.0f - ep) * rde;
+  float ta = -Ep * rde, tb = (1.0f - Ep) * rde;
   float t0 = fmaxf(fminf(ta, tb), 0.0f);
   float t1 = fminf(fmaxf(ta, tb), 1.0f);
-  float x0 = fmaf(t0, dx, xp), x1 = fmaf(t1, dx, xp);
-  float n0 = fminf(fmaxf(fmaf(t0, de, ep), 0.0f), 1.0f), n1 = fminf(fmaxf(fmaf(t1, de, ep), 0.0f), 1.0f);
-  float v = mean_pos(x0, x1) - mean_pos(x0 - (1.0f - n0), x1 - (1.0f - n1));
+  float X0 = fmaf(t0, dX, Xp), X1 = fmaf(t1, dX, Xp);
+  float H0 = fmaf(t0, dH, Hp), H1 = fmaf(t1, dH, Hp);
+  float v = 0.5f * (X0 + X1) - mean_pos(X0 - H0, X1 - H1) + mean_pos(lo - X0, lo - X1);
   v = de * (t1 - t0) * v;
   return (t1 > t0 && fabsf(de) > 1e-20f) ? v : 0.0f;
 }
 
+// a: corner offsets about its centroid (mx,my); triangle (o, o+e1, o+e2), invD = 1/(e1 x e2), aD = |e1 x e2|
 AIDET_HD float quad_tri_inter(const QuadRow& a, float ox, float oy, float e1x, float e1y, float e2x, float e2y,
                               float invD, float aD) {
-  float xi[4], et[4];
+  float cx = a.mx - ox, cy = a.my - oy;
+  float xc = (cx * e2y - cy * e2x) * invD, ec = (e1x * cy - e1y * cx) * invD;
+  float xref = fminf(fmaxf(xc, 0.0f), 1.0f);
+  float base = xc - xref, lo = -xref, hic = (1.0f - ec) - xref;
+  float X[4], E[4], Hh[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    float px = a.x[k] - ox, py = a.y[k] - oy;
-    xi[k] = (px * e2y - py * e2x) * invD;
-    et[k] = (e1x * py - e1y * px) * invD;
+    float dxi = (a.x[k] * e2y - a.y[k] * e2x) * invD;      // affine offsets of the corner about the centroid:
+    float det = (e1x * a.y[k] - e1y * a.x[k]) * invD;      // small for a small box, so differences stay accurate
+    X[k] = base + dxi; E[k] = ec + det; Hh[k] = hic - det;
   }
   float s = 0.0f;
 #pragma unroll
-  for (int k = 0; k < 4; k++) s += tri_edge(xi[k], et[k], xi[(k + 1) & 3], et[(k + 1) & 3]);
+  for (int k = 0; k < 4; k++) {
+    int q = (k + 1) & 3;
+    s += tri_edge(X[k], E[k], Hh[k], X[q], E[q], Hh[q], lo);
+  }
   return aD * s;
 }
 
@@ -213,7 +233,7 @@ AIDET_HD void quad_prepare(const float* box8, QuadRow* row, QuadCol* col) {
   for (int k = 0; k < 4; k++) { float dx = x[k] - mx, dy = y[k] - my; r2 = fmaxf(r2, dx * dx + dy * dy); }
   float rad = sqrtf(r2) * 1.000001f + 1e-5f * (fabsf(mx) + fabsf(my)) + 1e-6f;
   if (row) {
-    for (int k = 0; k < 4; k++) { row->x[k] = x[k]; row->y[k] = y[k]; }
+    for (int k = 0; k < 4; k++) { row->x[k] = x[k] - mx; row->y[k] = y[k] - my; }
     row->area = area; row->rad = rad; row->mx = mx; row->my = my;
     row->pad[0] = row->pad[1] = row->pad[2] = row->pad[3] = 0.0f;
   }

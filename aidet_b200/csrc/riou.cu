@@ -41,19 +41,16 @@ struct QuadKind {
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.my; }
 };
 
-// SWAP = false: matrix-row boxes are staged as Row records, matrix-column boxes live in
-// registers as Col records (frame = column box).  SWAP = true (IoF): the frame is the
-// matrix-row box, whose area is the denominator, which bounds the error by ~2 ulp of it.
-template <class K, bool SWAP>
+// Matrix-row boxes are staged as Row records (the box that is transformed), matrix-column
+// boxes live in registers as Col records (the box whose frame is used).
+template <class K>
 struct PairOp {
-  using S = typename std::conditional<SWAP, typename K::Col, typename K::Row>::type;   // staged (matrix row)
-  using R = typename std::conditional<SWAP, typename K::Row, typename K::Col>::type;   // registers (matrix col)
+  using S = typename K::Row;   // staged (matrix row)
+  using R = typename K::Col;   // registers (matrix col)
   __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) {
     float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
     if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;
-    float inter;
-    if constexpr (SWAP) inter = K::inter(r, s); else inter = K::inter(s, r);
-    return finish_overlap(inter, s.area, r.area, mode);
+    return finish_overlap(K::inter(s, r), s.area, r.area, mode);
   }
 };
 
@@ -74,13 +71,13 @@ __global__ void __launch_bounds__(256) riou_prepare_kernel(const float* __restri
 constexpr int kColsPerTile = 256;
 constexpr int kMaxTileRows = 64;
 
-template <class K, bool SWAP>
+template <class K>
 __global__ void __launch_bounds__(kColsPerTile)
-riou_matrix_kernel(const typename PairOp<K, SWAP>::S* __restrict__ rows, int m,
-                   const typename PairOp<K, SWAP>::R* __restrict__ cols, int n, int mode,
+riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
+                   const typename PairOp<K>::R* __restrict__ cols, int n, int mode,
                    float* __restrict__ out, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
                    int tiles_per_cta) {
-  using P = PairOp<K, SWAP>;
+  using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
   __shared__ __align__(128) S stage[2][kMaxTileRows];
   __shared__ __align__(8) uint64_t bar[2];
@@ -137,27 +134,21 @@ __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restri
   float pa[K::FMT], pb[K::FMT];
 #pragma unroll
   for (int k = 0; k < K::FMT; k++) { pa[k] = a[(size_t)i * K::FMT + k]; pb[k] = b[(size_t)i * K::FMT + k]; }
-  // frame = the box whose area is the denominator in IoF mode (a); symmetric for IoU
   typename K::Row r; typename K::Col c;
-  K::prepare(pb, &r, nullptr);
-  K::prepare(pa, nullptr, &c);
-  out[i] = PairOp<K, true>::overlap(c, r, mode);
+  K::prepare(pa, &r, nullptr);
+  K::prepare(pb, nullptr, &c);
+  out[i] = PairOp<K>::overlap(r, c, mode);
 }
 
-template <class K, bool SWAP>
+template <class K>
 static int launch_matrix(const float* a, int m, const float* b, int n, int mode, float* out, long long ld,
                          void* ws, int device, cudaStream_t s) {
-  using P = PairOp<K, SWAP>;
+  using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
   S* rows = reinterpret_cast<S*>(ws);
   R* cols = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)m * sizeof(S), 128));
-  if constexpr (SWAP) {
-    riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(a, m, nullptr, rows);
-    riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(b, n, cols, nullptr);
-  } else {
-    riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(a, m, rows, nullptr);
-    riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(b, n, nullptr, cols);
-  }
+  riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(a, m, rows, nullptr);
+  riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(b, n, nullptr, cols);
   const int sms = sm_count(device);
   const int n_col_tiles = ceil_div(n, kColsPerTile);
   int tile_rows = kMaxTileRows;
@@ -173,7 +164,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   grid = ceil_div(n_tiles, tiles_per_cta);
   {
     ProfScope prof(PROF_RIOU, s);
-    riou_matrix_kernel<K, SWAP><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, mode, out, ld, tile_rows,
+    riou_matrix_kernel<K><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, mode, out, ld, tile_rows,
                                                               n_row_tiles, n_tiles, tiles_per_cta);
   }
   count_launch(3);
@@ -207,12 +198,8 @@ int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt,
   }
   if (int rc = set_device(device)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (fmt == 5) {
-    return mode == AIDET_MODE_IOF ? launch_matrix<RectKind, true>(a, m, b, n, mode, out, ld_out, workspace, device, s)
-                                  : launch_matrix<RectKind, false>(a, m, b, n, mode, out, ld_out, workspace, device, s);
-  }
-  return mode == AIDET_MODE_IOF ? launch_matrix<QuadKind, true>(a, m, b, n, mode, out, ld_out, workspace, device, s)
-                                : launch_matrix<QuadKind, false>(a, m, b, n, mode, out, ld_out, workspace, device, s);
+  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, out, ld_out, workspace, device, s);
+  return launch_matrix<QuadKind>(a, m, b, n, mode, out, ld_out, workspace, device, s);
 }
 
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out, int device,

@@ -66,6 +66,20 @@ def thetaobb2pointobb(boxes):
     return torch.stack([x0, y0, x1, y1, 2 * cx - x0, 2 * cy - y0, 2 * cx - x1, 2 * cy - y1], dim=1).float()
 
 
+def free_quads(boxes, rel_noise=0.1, seed=0):
+    """(n,5) theta-OBBs -> (n,8) free convex quadrilaterals (what a point-OBB head regresses):
+    the rectangle's corners jittered by N(0, rel_noise * short side).  Returns (quads, convex mask)."""
+    g = _gen(seed)
+    p = thetaobb2pointobb(boxes)
+    short = torch.minimum(boxes[:, 2], boxes[:, 3])[:, None]
+    q = (p + torch.randn(p.shape, generator=g) * rel_noise * short).contiguous()
+    v = q.view(-1, 4, 2).double()
+    e = torch.roll(v, -1, 1) - v
+    cr = e[:, :, 0] * torch.roll(e, -1, 1)[:, :, 1] - e[:, :, 1] * torch.roll(e, -1, 1)[:, :, 0]
+    convex = (cr > 0).all(1) | (cr < 0).all(1)
+    return q, convex
+
+
 def multiclass_dets(n=2000, num_classes=15, side=1024, seed=2, dense=False, dim=5):
     """Config C2: (n, (C+1)*5) class-specific theta-OBBs and (n, C+1) softmax scores.
 

@@ -5,16 +5,23 @@
 #include "../../aidet_b200/csrc/geom.cuh"
 using namespace aidet;
 
+// mirrors PairOp<K>::overlap of riou.cu
 extern "C" void sim_riou_matrix(const float* a, int m, const float* b, int n, int fmt, int mode, float* out) {
   for (int i = 0; i < m; i++) {
     for (int j = 0; j < n; j++) {
       float v;
       if (fmt == 5) {
-        RectRow r; RectCol c; rect_prepare(a + 5 * (size_t)i, &r, nullptr); rect_prepare(b + 5 * (size_t)j, nullptr, &c);
-        v = rect_overlap(r, c, mode);
+        RectRow ra, rb; RectCol ca, cb;
+        rect_prepare(a + 5 * (size_t)i, &ra, &ca); rect_prepare(b + 5 * (size_t)j, &rb, &cb);
+        float dx = ra.cx - rb.cx, dy = ra.cy - rb.cy, rr = ra.rad + rb.rad;
+        if (dx * dx + dy * dy > rr * rr) v = 0.f;
+        else v = finish_overlap(rect_inter(ra, cb), ra.area, rb.area, mode);
       } else {
-        QuadRow r; QuadCol c; quad_prepare(a + 8 * (size_t)i, &r, nullptr); quad_prepare(b + 8 * (size_t)j, nullptr, &c);
-        v = quad_overlap(r, c, mode);
+        QuadRow ra, rb; QuadCol ca, cb;
+        quad_prepare(a + 8 * (size_t)i, &ra, &ca); quad_prepare(b + 8 * (size_t)j, &rb, &cb);
+        float dx = ra.mx - rb.mx, dy = ra.my - rb.my, rr = ra.rad + rb.rad;
+        if (dx * dx + dy * dy > rr * rr) v = 0.f;
+        else v = finish_overlap(quad_inter(ra, cb), ra.area, rb.area, mode);
       }
       out[(size_t)i * n + j] = v;
     }
