@@ -57,7 +57,12 @@ def test_axis_aligned_vs_oracle_and_torchvision(cuda, aligned, sample_num):
             tv = tv_roi_align(feat.double(), r2.double(), (out, out), scale, sample_num, aligned=False)
         else:
             tv = tv_roi_align(feat.double(), rois.double(), (out, out), scale, sample_num, aligned=True)
-        _close(got.cpu().numpy(), tv.numpy(), "fwd vs torchvision")
+        # torchvision (aligned=False) clamps the RoI to >= 1 feature px, the reference's v1 kernel does not
+        # (roi_align_kernel.cu:85-86 clamps at 0): the two agree exactly only for RoIs >= 1 px
+        big = (((rois[:, 3] + 1) * scale - rois[:, 1] * scale >= 1) & ((rois[:, 4] + 1) * scale - rois[:, 2] * scale >= 1))
+        assert aligned or big.sum() >= k // 2
+        sel = torch.ones(k, dtype=torch.bool) if aligned else big
+        _close(got.cpu().numpy()[sel.numpy()], tv.numpy()[sel.numpy()], "fwd vs torchvision")
 
 
 @pytest.mark.parametrize("aligned", [False, True])
