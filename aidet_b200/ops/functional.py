@@ -121,7 +121,7 @@ def _level_tables(tensors):
     return ptrs, Hs, Ws
 
 
-def rroi_align_forward(feats_nhwc, rois, scales, out_size, sample_num, variant, roi_level=None):
+def rroi_align_forward(feats_nhwc, rois, scales, out_size, sample_num, variant, roi_level=None, out=None):
     """feats_nhwc: list of (N,H_l,W_l,C) contiguous float32; rois (K,5|6) -> (K,ph,pw,C)."""
     ph, pw = out_size
     f0 = feats_nhwc[0]
@@ -131,7 +131,9 @@ def rroi_align_forward(feats_nhwc, rois, scales, out_size, sample_num, variant, 
         assert t.dtype == torch.float32 and t.is_contiguous() and t.size(0) == N and t.size(3) == C_
     rois = _f32c(rois, rois.size(-1), "rois")
     K = rois.size(0)
-    out = torch.empty((K, ph, pw, C_), dtype=torch.float32, device=f0.device)
+    if out is None:
+        out = torch.empty((K, ph, pw, C_), dtype=torch.float32, device=f0.device)
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == (K, ph, pw, C_)
     if K == 0:
         return out
     lvl = None if roi_level is None else roi_level.to(device=f0.device, dtype=torch.int32).contiguous()

@@ -1,0 +1,667 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the OBB hot path on B200 (one JSON line on stdout, rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|iou|nms|roi]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): rotated IoU Gpairs/s, rotated-NMS Mboxes/s, RoIAlign GB/s.  The line's
+top-level `metric`/`value` is the rotated-IoU matrix (first named, config C4: 100k x 100k, dense
+synthetic set -- every pair truly intersects, so the bounding-circle early-out never fires and the
+256 flop/pair charge is earned); the NMS (config C2) and RoIAlign (config C3) figures ride in the
+`nms` and `roialign` objects of the same line, each with its own roofline, e2e and cpu_baseline.
+
+A "step" is one pass of the op over one batch of synthetic input that is already resident in HBM;
+`e2e` repeats it through the public Python API with pinned HOST buffers, H2D and D2H copies inside
+the timed region.  N > 1: IoU rows are sharded over the ranks (strong scaling of the same 100k x
+100k problem) and the shard results are exchanged with one in-place NCCL all-gather, which IS inside
+the timed region (`compute_only` gives the figure without it); NMS groups and RoIs are sharded with
+no data-path collective.
+
+--impl reference times the CPU implementation of the same path on the host cores (the reference
+has no in-tree rotated IoU/NMS/RoIAlign -- see DESIGN.md -- so this is the float64 oracle port under
+oracle/, with OpenMP over all cores, on a bounded sample of the same workload; the reference's own
+axis-aligned nms_cpu.cpp, compiled unmodified into oracle/_ref, is timed beside it).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F_PAIR = 256.0                       # FP32 flop charged per box pair
+FP32_PEAK_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4 TFLOP/s at the 1965 MHz maximum clock
+SCALES = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="all", choices=["all", "iou", "nms", "roi"])
+    p.add_argument("--iou-n", type=int, default=100000, help="IoU matrix side (config C4: 100000)")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 100 ms while the timed regions run (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            # "under load" = samples in the upper half of the power range seen
+            thr = (max(pw) + min(pw)) / 2 if pw else 0
+            load = [s for s, w in zip(sm, pw) if w >= thr] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), power_w_max=max(pw),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------ distributed plumbing
+class Dist:
+    def __init__(self, args):
+        import torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.on = self.world > 1
+        if self.on and args.impl == "ours":
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.on:
+            self.dist.barrier()
+
+    def max_float(self, x, device):
+        import torch
+        if not self.on:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_float(self, x, device):
+        import torch
+        if not self.on:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def finish(self):
+        if self.on and hasattr(self, "dist"):
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed(D, dev, steps, warmup, fn, flush=None):
+    """W untimed + K timed calls of fn(); barrier + synchronize on both sides; device time via CUDA
+    events on the launching stream; returns (max-over-ranks total ms of the K steps, launches of ours)."""
+    import torch
+    from aidet_b200 import _lib as L
+    for _ in range(warmup):
+        if flush is not None:
+            flush()
+        fn()
+    torch.cuda.synchronize(dev)
+    D.barrier()
+    torch.cuda.synchronize(dev)
+    l0 = L.launch_count()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = L.launch_count() - l0
+    D.barrier()
+    torch.cuda.synchronize(dev)
+    return D.max_float(ms, dev), launches
+
+
+def wall_timed(D, dev, steps, warmup, fn):
+    """End-to-end legs: host wall clock around K calls that each end with the result on the host."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize(dev)
+    ms = (time.perf_counter() - t0) * 1e3
+    D.barrier()
+    return D.max_float(ms, dev)
+
+
+# ------------------------------------------------------------------ workloads
+def iou_inputs(n, dense=True):
+    from aidet_b200 import synth
+    a, _ = synth.dota_boxes(n, side=16384, seed=4, dense=dense)
+    b, _ = synth.dota_boxes(n, side=16384, seed=5, dense=dense)
+    return a, b
+
+
+def nms_inputs(dense=False, images=1):
+    """Config C2 candidates: 2000 proposals x 15 classes, score > 0.05 (rbbox_nms.py:30); `images`
+    tiles are batched as images x classes groups."""
+    import torch
+    from aidet_b200 import synth
+    bs, ss, gs = [], [], []
+    for im in range(images):
+        mb, msc = synth.multiclass_dets(2000, 15, seed=2 + im, dense=dense)
+        n, C = msc.shape[0], 15
+        boxes = mb.view(n, C + 1, 5)[:, 1:]
+        valid = (msc[:, 1:] > 0.05).t()
+        lab, rows = valid.nonzero(as_tuple=True)
+        bs.append(boxes[rows, lab]); ss.append(msc[:, 1:][rows, lab]); gs.append(lab.int() + 15 * im)
+    return torch.cat(bs).contiguous(), torch.cat(ss).contiguous(), torch.cat(gs).contiguous(), 15 * images
+
+
+def group_pairs(groups, n_groups):
+    import torch
+    cnt = torch.bincount(groups.long(), minlength=n_groups).double()
+    return float((cnt * (cnt - 1) / 2).sum().item())
+
+
+def roi_touched_bytes(rois, lvl, batch, C, tile=1024):
+    """Exact |U_l| (distinct feature pixels touched by any bilinear tap) from the oracle, level by level."""
+    import numpy as np
+    from oracle import oracle as O
+    total = 0
+    for l, s in enumerate(SCALES):
+        sel = (lvl == l).nonzero().flatten()
+        if sel.numel() == 0:
+            continue
+        hw = int(tile * s)
+        dummy = np.zeros((batch, hw, hw, 1), np.float32)
+        _, touched = O.roi_align_fwd(dummy, rois[sel].numpy(), s, (7, 7), 2, O.ROI_V2_ALIGNED, want_touched=True)
+        total += int(touched.sum())
+    return total
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args, D):
+    import torch
+    from aidet_b200 import _lib as L, synth
+    from aidet_b200.ops import functional as Fn
+    dev = torch.device("cuda", D.local)
+    torch.cuda.set_device(dev)
+    hbm_peak, hbm_src = measured_peaks()
+    G, r = D.world, D.rank
+    line = {}
+    sampler = ClockSampler(D.local) if r == 0 else None
+    L.prof_enable(True)
+    ffma = L.ffma_peak_tflops(D.local, 8192)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    # ---------------- rotated IoU (C4), rows sharded over the ranks
+    if args.workload in ("all", "iou"):
+        n = args.iou_n
+        a, b = iou_inputs(n, dense=True)
+        rows_per = (n + G - 1) // G
+        m_pad = rows_per * G
+        a_pad = torch.cat([a, a[: m_pad - n]]) if m_pad > n else a
+        a_dev, b_dev = a_pad.to(dev), b.to(dev)
+        my = a_dev[r * rows_per:(r + 1) * rows_per].contiguous()
+        out = torch.empty((m_pad, n), dtype=torch.float32, device=dev)      # N=1: 40 GB >> L2, no flush needed
+        shard = out[r * rows_per:(r + 1) * rows_per]
+
+        def step_compute():
+            Fn.riou_matrix(my, b_dev, out=shard)
+
+        def step_full():
+            Fn.riou_matrix(my, b_dev, out=shard)
+            if D.on:
+                D.dist.all_gather_into_tensor(out, shard)
+
+        L.prof_read(L.PROF_RIOU, reset=True)
+        ms, launches = timed(D, dev, args.steps, args.warmup, step_full)
+        k_ms, k_cnt = L.prof_read(L.PROF_RIOU, reset=True)
+        k_ms_avg = D.max_float(k_ms / max(k_cnt, 1), dev)
+        pairs = float(n) * n
+        ms_step = ms / args.steps
+        comp_ms = ms_step
+        if D.on:
+            cms, _ = timed(D, dev, args.steps, args.warmup, step_compute)
+            comp_ms = cms / args.steps
+        kernel_pairs = float(rows_per) * n                                   # per launch, per rank
+        achieved = kernel_pairs * F_PAIR / (k_ms_avg * 1e-3) / 1e12
+        line.update({
+            "metric": "rotated IoU Gpairs/s", "value": pairs / ms_step / 1e6, "unit": "Gpairs/s",
+            "n_gpus": G, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4 rotated IoU matrix %dx%d theta-OBB (cx,cy,w,h,theta), dense synthetic set, "
+                                   "rows sharded over %d GPU(s)%s" % (n, n, G, " + in-place NCCL all-gather" if D.on else ""),
+                       "rows_per_rank": rows_per, "l2": "output %.1f GB per step >> 126 MB L2 (no flush needed)"
+                                                        % (rows_per * n * 4 / 1e9)},
+            "compute_only": {"value": pairs / comp_ms / 1e6, "unit": "Gpairs/s", "ms_per_step": comp_ms},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp32-alu", "achieved": achieved, "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s",
+                         "frac": achieved / FP32_PEAK_NOMINAL, "traffic": None,
+                         "kernel": "riou_matrix_kernel<RectKind>", "kernel_ms": k_ms_avg,
+                         "flop_per_pair": F_PAIR, "pairs_per_launch": kernel_pairs,
+                         "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz (nominal max clock); FFMA micro-benchmark "
+                                        "on this box: %.1f TFLOP/s" % ffma,
+                         "frac_of_measured_ffma": achieved / ffma,
+                         "hbm_write_gbs": kernel_pairs * 4 / (k_ms_avg * 1e-3) / 1e9},
+        })
+        # DOTA-shaped (sparse) set: pairs/s only, no roofline fraction
+        ns = min(n, 32768)
+        sa, sb = iou_inputs(ns, dense=False)
+        sa, sb = sa.to(dev), sb.to(dev)
+        rs = (ns + G - 1) // G
+        so = out.view(-1)[: rs * ns].view(rs, ns)
+        sm_, _ = timed(D, dev, args.steps, args.warmup, lambda: Fn.riou_matrix(sa[r * rs:(r + 1) * rs], sb, out=so))
+        line["dota_shaped"] = {"value": float(ns) * ns / (sm_ / args.steps) / 1e6, "unit": "Gpairs/s",
+                               "workload": "%dx%d DOTA-shaped (clustered, sparse) boxes, compute only" % (ns, ns)}
+
+        if not args.no_e2e:
+            # e2e: boxes in pinned host memory -> H2D -> kernel -> D2H of the result, streamed in row
+            # chunks through two pinned staging buffers (the full fp32 result is 40 GB).
+            chunk = max(1, min(rows_per, (1 << 30) // (4 * n)))              # ~1 GiB of result per chunk
+            a_host = my.cpu().pin_memory()
+            b_host = b.pin_memory()
+            stage = [torch.empty((chunk, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+            dbuf = [torch.empty((chunk, n), dtype=torch.float32, device=dev) for _ in range(2)]
+            copy_stream = torch.cuda.Stream(dev)
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            checksum = [0.0]
+
+            def e2e_step():
+                ad = a_host.to(dev, non_blocking=True)
+                bd = b_host.to(dev, non_blocking=True)
+                cur = torch.cuda.current_stream(dev)
+                for ci, r0 in enumerate(range(0, rows_per, chunk)):
+                    k = ci & 1
+                    rr = min(chunk, rows_per - r0)
+                    done[k].synchronize()                                     # staging buffer k is free again
+                    Fn.riou_matrix(ad[r0:r0 + rr], bd, out=dbuf[k][:rr])
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(ev)
+                        stage[k][:rr].copy_(dbuf[k][:rr], non_blocking=True)
+                        done[k].record(copy_stream)
+                copy_stream.synchronize()
+                checksum[0] = float(stage[0][0, 0])
+
+            ems = wall_timed(D, dev, max(2, min(args.steps, 3)), 1, e2e_step)
+            esteps = max(2, min(args.steps, 3))
+            line["e2e"] = {"value": pairs / (ems / esteps) / 1e6, "unit": "Gpairs/s",
+                           "h2d_bytes_per_step": int((rows_per + n) * 5 * 4),
+                           "d2h_bytes_per_step": int(rows_per * n * 4), "ms_per_step": ems / esteps,
+                           "steps": esteps,
+                           "how": "pinned host boxes -> H2D -> riou_matrix per %d-row chunk -> D2H into pinned staging "
+                                  "(double-buffered, copy stream); per rank: its row shard" % chunk}
+            del stage, dbuf
+        del out, shard
+        torch.cuda.empty_cache()
+
+    # ---------------- batched rotated NMS (C2)
+    if args.workload in ("all", "nms"):
+        nms = {}
+        for tag, dense, images in (("c2", False, 1), ("c2_dense", True, 1), ("c2x8_dense", True, 8)):
+            cb, cs, cg, ng = nms_inputs(dense=dense, images=images)
+            # shard groups over ranks (independent units, no data-path collective)
+            mine = (cg % G) == r if G > 1 else torch.ones_like(cg, dtype=torch.bool)
+            cbd, csd, cgd = cb[mine].to(dev), cs[mine].to(dev), cg[mine].to(dev)
+            L.prof_read(L.PROF_NMS_MASK, reset=True)
+            ms, launches = timed(D, dev, args.steps, args.warmup,
+                                 lambda: Fn.nms_batched(cbd, csd, cgd, 0.5, n_groups=ng), flush=flush)
+            k_ms, k_cnt = L.prof_read(L.PROF_NMS_MASK, reset=True)
+            k_avg = D.max_float(k_ms / max(k_cnt, 1), dev)
+            nb = D.sum_float(float(cbd.shape[0]), dev)
+            gp = group_pairs(cg[mine], ng)
+            ach = gp * F_PAIR / (k_avg * 1e-3) / 1e12
+            nms[tag] = {"value": nb / (ms / args.steps) / 1e3, "unit": "Mboxes/s", "ms_per_step": ms / args.steps,
+                        "boxes": int(nb), "groups": ng, "gpu_launches": int(launches),
+                        "roofline": {"bound": "fp32-alu", "achieved": ach, "peak": FP32_PEAK_NOMINAL,
+                                     "unit": "TFLOP/s", "frac": ach / FP32_PEAK_NOMINAL, "kernel": "nms_mask_kernel<NmsRect>",
+                                     "kernel_ms": k_avg, "charged_pairs_per_launch": gp, "traffic": None}}
+        nms["workload"] = ("C2: 2000 proposals x 15 classes, score>0.05 candidates, thr 0.5, one launch over all "
+                           "classes (c2 = DOTA-shaped, c2_dense = every pair intersects, c2x8 = 8 tiles batched); "
+                           "L2 flushed between steps; time = sort+gather+mask+scan+compact+count readback")
+        if not args.no_e2e:
+            import numpy as np
+            from aidet_b200.ops import batched_rnms
+            cb, cs, cg, ng = nms_inputs(dense=False, images=1)
+            hb, hs, hg = cb.pin_memory(), cs.pin_memory(), cg.pin_memory()
+
+            def nms_e2e():
+                k = batched_rnms(hb.to(dev, non_blocking=True), hs.to(dev, non_blocking=True),
+                                 hg.to(dev, non_blocking=True), 0.5, n_groups=ng)
+                return k.cpu()
+            ems = wall_timed(D, dev, args.steps, args.warmup, nms_e2e)
+            kk = nms_e2e()
+            nms["e2e"] = {"value": cb.shape[0] / (ems / args.steps) / 1e3, "unit": "Mboxes/s",
+                          "h2d_bytes_per_step": int(cb.numel() * 4 + cs.numel() * 4 + cg.numel() * 4),
+                          "d2h_bytes_per_step": int(kk.numel() * 8 + 4), "ms_per_step": ems / args.steps,
+                          "how": "c2: pinned host boxes/scores/groups -> batched_rnms -> keep indices on the host"}
+        line["nms"] = nms
+
+    # ---------------- rotated RoIAlign fwd + bwd (C3)
+    if args.workload in ("all", "roi"):
+        feats_h = synth.fpn_features()
+        rois_h, lvl_h = synth.rotated_rois()
+        feats = [f.to(dev) for f in feats_h]
+        rois, lvl = rois_h.to(dev), lvl_h.to(dev)
+        K, C = rois.shape[0], feats[0].shape[3]
+        out = Fn.rroi_align_forward(feats, rois, SCALES, (7, 7), 2, 2, lvl)
+        go = torch.randn(out.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+        grads = [torch.empty_like(f) for f in feats]
+        touched = roi_touched_bytes(rois_h, lvl_h, feats_h[0].shape[0], C)
+        feat_elems = sum(f.numel() for f in feats)
+        bytes_fwd = 4.0 * (C * touched + K * 49 * C + 6 * K)
+        bytes_bwd = 4.0 * (K * 49 * C + C * touched + 6 * K) + 4.0 * feat_elems
+
+        def fwd():
+            Fn.rroi_align_forward(feats, rois, SCALES, (7, 7), 2, 2, lvl, out=out)
+
+        def bwd():
+            for g_ in grads:
+                g_.zero_()
+            Fn.rroi_align_backward(go, grads, rois, SCALES, 2, 2, lvl)
+
+        L.prof_read(L.PROF_ROI_FWD, reset=True)
+        fms, fl = timed(D, dev, args.steps, args.warmup, fwd, flush=flush)
+        kf, kfc = L.prof_read(L.PROF_ROI_FWD, reset=True)
+        L.prof_read(L.PROF_ROI_BWD, reset=True)
+        bms, bl = timed(D, dev, args.steps, args.warmup, bwd, flush=flush)
+        kb, kbc = L.prof_read(L.PROF_ROI_BWD, reset=True)
+        fms, bms = fms / args.steps, bms / args.steps
+        tot_bytes = (bytes_fwd + bytes_bwd) * G
+        roi = {"value": tot_bytes / ((fms + bms) * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": fms + bms,
+               "fwd": {"ms": fms, "gbs": bytes_fwd * G / (fms * 1e-3) / 1e9, "bytes": bytes_fwd,
+                       "kernel_ms": kf / max(kfc, 1)},
+               "bwd": {"ms": bms, "gbs": bytes_bwd * G / (bms * 1e-3) / 1e9, "bytes": bytes_bwd,
+                       "kernel_ms": kb / max(kbc, 1), "includes": "zero-fill of grad features"},
+               "gpu_launches": int(fl + bl), "scaling": "weak (replicas: every rank runs the full C3 batch)",
+               "workload": "C3: %d rotated RoIs (512/img x 8), 7x7, C=%d, FPN P2-P5 of a 1024 tile, NHWC fp32, "
+                           "sample_num 2, all levels in one launch; features %.1f MB > L2 and L2 flushed between steps"
+                           % (K, C, feat_elems * 4 / 1e6),
+               "touched_feature_pixels": touched,
+               "roofline": {"bound": "hbm", "achieved": (bytes_fwd + bytes_bwd) / ((fms + bms) * 1e-3) / 1e9,
+                            "peak": hbm_peak, "unit": "GB/s",
+                            "frac": (bytes_fwd + bytes_bwd) / ((fms + bms) * 1e-3) / 1e9 / hbm_peak,
+                            "peak_source": hbm_src, "traffic": None,
+                            "fwd_frac": bytes_fwd / (fms * 1e-3) / 1e9 / hbm_peak,
+                            "bwd_frac": bytes_bwd / (bms * 1e-3) / 1e9 / hbm_peak}}
+        if not args.no_e2e:
+            fh = [f.pin_memory() for f in feats_h]
+            rh, lh = rois_h.pin_memory(), lvl_h.pin_memory()
+            goh = go.cpu().pin_memory()
+            out_h = torch.empty(out.shape, dtype=torch.float32).pin_memory()
+            gh = [torch.empty(f.shape, dtype=torch.float32).pin_memory() for f in feats_h]
+
+            def roi_e2e():
+                fd = [f.to(dev, non_blocking=True) for f in fh]
+                rd, ld = rh.to(dev, non_blocking=True), lh.to(dev, non_blocking=True)
+                gd = goh.to(dev, non_blocking=True)
+                o = Fn.rroi_align_forward(fd, rd, SCALES, (7, 7), 2, 2, ld)
+                out_h.copy_(o, non_blocking=True)
+                gr = [torch.zeros_like(f) for f in fd]
+                Fn.rroi_align_backward(gd, gr, rd, SCALES, 2, 2, ld)
+                for hbuf, g_ in zip(gh, gr):
+                    hbuf.copy_(g_, non_blocking=True)
+                torch.cuda.synchronize(dev)
+            es = max(2, min(args.steps, 5))
+            ems = wall_timed(D, dev, es, 1, roi_e2e)
+            h2d = feat_elems * 4 + rois_h.numel() * 4 + lvl_h.numel() * 4 + go.numel() * 4
+            d2h = out.numel() * 4 + feat_elems * 4
+            roi["e2e"] = {"value": tot_bytes / (ems / es * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": int(d2h), "ms_per_step": ems / es, "steps": es,
+                          "how": "pinned host features+rois+grad_out -> H2D -> fwd -> D2H out; zero-fill + bwd -> D2H grads"}
+        line["roialign"] = roi
+
+    line["clocks"] = sampler.stop() if sampler else None
+    line["ffma_peak_tflops_measured"] = ffma
+    return line, dev
+
+
+# ------------------------------------------------------------------ CPU legs (oracle = checker / baseline only)
+def cpu_iou(sample, threads=None):
+    from oracle import oracle as O
+    a, b = iou_inputs(sample, dense=True)
+    an, bn = a.numpy(), b.numpy()
+    O.riou_matrix(an[:64], bn[:64])
+    t0 = time.perf_counter()
+    O.riou_matrix(an, bn)
+    dt = time.perf_counter() - t0
+    return float(sample) * sample / dt / 1e9, dt
+
+
+def cpu_nms(dense=False):
+    """float64 oracle greedy NMS, the 15 class groups spread over the host threads (the reference's
+    mergebypoly_mp likewise maps classes over a process pool, dota.py:336)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    cb, cs, cg, ng = nms_inputs(dense=dense, images=1)
+    cbn, csn, cgn = cb.numpy(), cs.numpy(), cg.numpy()
+    parts = [np.nonzero(cgn == g)[0] for g in range(ng)]
+    O.nms(cbn[:32], csn[:32], 0.5, plus_one=False)
+
+    def one(idx):
+        return O.nms(cbn[idx], csn[idx], 0.5, cmp_ge=False, plus_one=False)[0]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
+        list(ex.map(one, parts))
+    dt = time.perf_counter() - t0
+    return cbn.shape[0] / dt / 1e6, dt, cbn.shape[0]
+
+
+def cpu_nms_reference_hbb():
+    """The reference's own nms_cpu.cpp (oracle/_ref, compiled unmodified) on the AABB envelopes, per class."""
+    import torch
+    from oracle import build_ref
+    mod = build_ref.load()
+    if mod is None:
+        return None
+    from aidet_b200 import synth
+    cb, cs, cg, ng = nms_inputs(dense=False, images=1)
+    p = synth.thetaobb2pointobb(cb).view(-1, 4, 2)
+    hbb = torch.cat([p.min(1)[0], p.max(1)[0]], 1)
+    dets = torch.cat([hbb, cs[:, None]], 1)
+    parts = [dets[cg == g].contiguous() for g in range(ng)]
+    mod.nms(parts[0][:16], 0.5)
+    t0 = time.perf_counter()
+    for d in parts:
+        if d.shape[0]:
+            mod.nms(d, 0.5)
+    dt = time.perf_counter() - t0
+    return dets.shape[0] / dt / 1e6, dt
+
+
+def cpu_roi(sample_rois=512):
+    """float64 oracle rotated RoIAlign fwd + bwd (OpenMP) on the first `sample_rois` RoIs of C3, level by level."""
+    import numpy as np
+    import torch
+    from aidet_b200 import synth
+    from oracle import oracle as O
+    feats = synth.fpn_features()
+    rois, lvl = synth.rotated_rois()
+    rois, lvl = rois[:sample_rois], lvl[:sample_rois]
+    C = feats[0].shape[3]
+    go = np.random.RandomState(0).randn(sample_rois, 7, 7, C).astype(np.float32)
+    touched = roi_touched_bytes(rois, lvl, feats[0].shape[0], C)
+    t0 = time.perf_counter()
+    for l, s in enumerate(SCALES):
+        sel = (lvl == l).nonzero().flatten()
+        if sel.numel() == 0:
+            continue
+        O.roi_align_fwd(feats[l].numpy(), rois[sel].numpy(), s, (7, 7), 2, O.ROI_V2_ALIGNED)
+        O.roi_align_bwd(go[sel.numpy()], tuple(feats[l].shape), rois[sel].numpy(), s, 2, O.ROI_V2_ALIGNED)
+    dt = time.perf_counter() - t0
+    K = sample_rois
+    by = 4.0 * (C * touched + K * 49 * C + 6 * K) * 2 + 4.0 * sum(f.numel() for f in feats)
+    return by / dt / 1e9, dt
+
+
+def cpu_baselines(args):
+    cores = os.cpu_count()
+    out = {}
+    if args.workload in ("all", "iou"):
+        v, dt = cpu_iou(8192)
+        out["iou"] = {"value": v, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+                      "sample": "8192x8192 block of the same dense set, float64 oracle (oracle/oracle_geom.c), OpenMP, %.1f s" % dt}
+    if args.workload in ("all", "nms"):
+        v, dt, nb = cpu_nms(False)
+        out["nms"] = {"value": v, "unit": "Mboxes/s", "cores": min(cores, 15), "kind": "port",
+                      "sample": "full C2 (%d candidates, 15 classes over a thread pool), float64 oracle, %.2f s" % (nb, dt)}
+        ref = cpu_nms_reference_hbb()
+        if ref is not None:
+            out["nms_hbb_reference"] = {"value": ref[0], "unit": "Mboxes/s", "cores": 1, "kind": "reference",
+                                        "sample": "reference nms_cpu.cpp (unmodified, oracle/_ref) on the AABB envelopes "
+                                                  "of C2, class by class, %.3f s" % ref[1]}
+    if args.workload in ("all", "roi"):
+        v, dt = cpu_roi(512)
+        out["roialign"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
+                           "sample": "first 512 of the 4096 C3 RoIs, fwd+bwd, float64 oracle (oracle/oracle_roi.c), OpenMP, %.1f s" % dt}
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the host cores, same metric/config keys as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cores = os.cpu_count()
+    n = args.iou_n
+    sample = 4096
+    for _ in range(args.warmup):
+        cpu_iou(1024)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, _dt = cpu_iou(sample)
+        vals.append(v)
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    value = statistics.median(vals)
+    line = {"impl": "reference", "metric": "rotated IoU Gpairs/s", "value": value, "unit": "Gpairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 rotated IoU matrix %dx%d theta-OBB, dense synthetic set; each step = a %dx%d "
+                                   "block of it on the host CPU" % (n, n, sample, sample)},
+            "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+                             "sample": "%dx%d block per step, float64 oracle port (the reference has no in-tree rotated "
+                                       "IoU; wwtool/polyiou is un-vendored), OpenMP over all cores" % (sample, sample)},
+            "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if args.workload in ("all", "nms"):
+        v, dt, nb = cpu_nms(False)
+        line["nms"] = {"value": v, "unit": "Mboxes/s", "cores": min(cores, 15), "kind": "port",
+                       "sample": "full C2, %d candidates" % nb, "ms_per_step": dt * 1e3}
+        ref = cpu_nms_reference_hbb()
+        if ref is not None:
+            line["nms"]["hbb_reference"] = {"value": ref[0], "unit": "Mboxes/s", "cores": 1, "kind": "reference"}
+    if args.workload in ("all", "roi"):
+        v, dt = cpu_roi(512)
+        line["roialign"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
+                            "sample": "first 512 C3 RoIs fwd+bwd", "ms_per_step": dt * 1e3}
+    return line
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        line = run_reference(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: aidet_b200 has no CPU path (use --impl reference for the CPU arm)")
+    D = Dist(args)
+    line, dev = run_ours(args, D)
+    if D.rank == 0 and not args.no_cpu and D.world == 1:
+        cb = cpu_baselines(args)
+        if "iou" in cb:
+            line["cpu_baseline"] = cb.pop("iou")
+        for k, v in cb.items():
+            tgt = {"nms": "nms", "nms_hbb_reference": "nms", "roialign": "roialign"}[k]
+            if tgt in line:
+                line[tgt]["cpu_baseline" if k != "nms_hbb_reference" else "cpu_baseline_hbb_reference"] = v
+    if D.rank == 0:
+        print(json.dumps(line), flush=True)
+    D.finish()
+
+
+if __name__ == "__main__":
+    main()
