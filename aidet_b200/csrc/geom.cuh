@@ -46,19 +46,16 @@ AIDET_HD float fdiv(float a, float b) { return a / b; }
 enum { MODE_IOU = 0, MODE_IOF = 1 };
 
 // ---------------------------------------------------------------- records
-// theta-OBB, prepared once per box by the prologue kernel (32 B each).
-struct AIDET_ALIGN16 RectRow {   // the box that is transformed ("A")
+// theta-OBB, prepared once per box by the prologue kernel (32 B).  The same record serves
+// as "A" (the box that is transformed) and as "B" (the box whose frame is used).
+struct AIDET_ALIGN16 Rect {     // first 16 B: all the bounding-circle test needs (one LDS.128)
   float cx, cy;                  // centre
-  float ux, uy;                  // half-axis  (w/2)( cos,  sin)
-  float vx, vy;                  // half-axis  (h/2)(-sin,  cos)
-  float area, rad;               // w*h, circumradius
-};
-struct AIDET_ALIGN16 RectCol {   // the box whose frame is used ("B")
-  float cx, cy;
-  float c, s;                    // cos, sin
+  float rad, area;               // circumradius (slightly inflated), w*h
+  float c, s;                    // cos, sin of theta
   float W, H;                    // half extents
-  float area, rad;
 };
+using RectRow = Rect;
+using RectCol = Rect;
 
 // point-OBB (general simple quad), 64 B each.
 struct AIDET_ALIGN16 QuadRow {
@@ -79,81 +76,95 @@ struct AIDET_ALIGN16 HbbBox { float x1, y1, x2, y2; };
 
 // ------------------------------------------------- rect ^ rect (theta-OBB)
 
-// Edge integral described in the header comment, for the edge p + t d, t in [0,1].
-//   hdx, hdy : half of the edge vector (tiny-guarded), rdx, rdy : 1/dx, 1/dy
-//   x1st, x2nd : the slab bounds in the order this edge direction meets them
-//                (x-lo, x-hi if dx > 0, swapped otherwise); Hs = copysign(H, dy)
-// The in-slab parameter range [t0,t1] is split at the two x crossings into a "before"
-// piece (clamp value x1st), an inside piece (value = x at its middle) and an "after"
-// piece (value x2nd).  All piece lengths are max(0, .) of differences, so an empty
-// range contributes exactly 0 without a branch.
-AIDET_HD float rect_edge(float px, float py, float hdx, float hdy, float rdx, float rdy, float x1st, float x2nd,
-                         float Hs) {
-  float t0 = fmaxf((-Hs - py) * rdy, 0.0f);
-  float t1 = fminf((Hs - py) * rdy, 1.0f);
-  float xa = (x1st - px) * rdx, xb = (x2nd - px) * rdx;      // xa <= xb
-  float i0 = fmaxf(t0, xa), i1 = fminf(t1, xb);
-  float tin = fmaxf(i1 - i0, 0.0f);
-  float tbe = fmaxf(fminf(t1, xa) - t0, 0.0f);
-  float taf = fmaxf(t1 - fmaxf(t0, xb), 0.0f);
-  float xmid = fmaf(hdx, i0 + i1, px);
-  return hdy * fmaf(taf, x2nd, fmaf(tbe, x1st, tin * xmid));
+// Edge integral described in the header comment for the edge p + tau * dir, tau in [0, L],
+// |dir| = 1 (tau is arc length, so no per-box reciprocal is needed: the crossing parameters
+// only use 1/cos and 1/sin of the RELATIVE angle, two MUFU.RCP per pair for all four edges).
+//   qy = -py / dir.y,  hr = H / |dir.y|        -> in-slab range  [qy - hr, qy + hr] ^ [0, L]
+//   qx = -px / dir.x,  a1 <= a2                -> x crossings    qx + a1, qx + a2
+//   x1st, x2nd : the box's x bounds in the order this direction meets them
+//   hdx = dir.x / 2
+// Inside [t0,t1] the clamp value is x1st before the first crossing, x2nd after the second and
+// x itself (taken at the middle of the piece) in between.  Every piece length is a difference
+// of clamped parameters, so an empty range contributes exactly 0 without a branch.
+AIDET_HD float rect_edge(float px, float qy, float hr, float L, float qx, float a1, float a2, float x1st,
+                         float x2nd, float hdx) {
+  float t0 = fmaxf(qy - hr, 0.0f);
+  float t1 = fmaxf(fminf(qy + hr, L), t0);
+  float ta = fminf(fmaxf(qx + a1, t0), t1);
+  float tb = fminf(fmaxf(qx + a2, t0), t1);
+  float xmid = fmaf(hdx, ta + tb, px);
+  return fmaf(tb - ta, xmid, fmaf(t1 - tb, x2nd, (ta - t0) * x1st));
 }
 
-AIDET_HD float guard_tiny(float d) { return (fabsf(d) > 1e-18f) ? d : 1e-18f; }
-
-// Intersection area of A (row record) with B (col record).
-AIDET_HD float rect_inter(const RectRow& a, const RectCol& b) {
-  float relx = a.cx - b.cx, rely = a.cy - b.cy;
-  // rotate by -theta_b
-  float rx = fmaf(b.c, relx, b.s * rely), ry = fmaf(b.c, rely, -b.s * relx);
-  float ux = guard_tiny(fmaf(b.c, a.ux, b.s * a.uy)), uy = guard_tiny(fmaf(b.c, a.uy, -b.s * a.ux));
-  float vx = guard_tiny(fmaf(b.c, a.vx, b.s * a.vy)), vy = guard_tiny(fmaf(b.c, a.vy, -b.s * a.vx));
-  // Shift x by xref = clamp(rx): the contour integral of a constant times 1[|y|<=H] dy over
-  // a closed polygon is 0, so the result is unchanged, but every term is now of the order
-  // of the SMALLER box, which keeps the rounding error relative to the intersection.
-  float xref = fminf(fmaxf(rx, -b.W), b.W);
-  float xlo = -b.W - xref, xhi = b.W - xref;
-  rx -= xref;
+// Intersection area of A with B, in B's frame.
+AIDET_HD float rect_inter(const Rect& a, const Rect& b) {
+  const float relx = a.cx - b.cx, rely = a.cy - b.cy;
+  // centre of A and its axis direction (cos, sin of the relative angle) in B's frame.  The tiny
+  // addend (applied last, so it cannot be absorbed) keeps both components non-zero -- parallel
+  // boxes would give 1/0 -- and is far below f32 resolution of any other value.
+  float rx = fmaf(b.c, relx, b.s * rely);
+  const float ry = fmaf(b.c, rely, -b.s * relx);
+  const float c = fmaf(a.c, b.c, a.s * b.s) + 1e-20f;
+  const float s = fmaf(a.s, b.c, -a.c * b.s) + 1e-20f;
+  // Shift x by xref = clamp(rx): the contour integral of a constant times 1[|y|<=H] dy over a
+  // closed polygon is 0, so the result is unchanged, but every term is now of the order of the
+  // SMALLER box, which keeps the rounding error relative to the intersection.
+  const float xref = fminf(fmaxf(rx, -b.W), b.W);
+  rx -= xref;                                     // B now spans [-xref - W, -xref + W] in x
+  const float ux = a.W * c, uy = a.W * s, vx = -a.H * s, vy = a.H * c;
   // corners p0 = r-u-v, p1 = r+u-v, p3 = r-u+v  (CCW: p0,p1,p2,p3)
-  float mx = rx - ux, my = ry - uy;
-  float p0x = mx - vx, p0y = my - vy;
-  float p3x = mx + vx, p3y = my + vy;
-  float p1x = (rx + ux) - vx, p1y = (ry + uy) - vy;
-  // edge vectors are +-2u, +-2v:  1/(2u) = 0.5/u
-  float rux = 0.5f * frcp(ux), ruy = 0.5f * frcp(uy), rvx = 0.5f * frcp(vx), rvy = 0.5f * frcp(vy);
-  float u1 = ux > 0.0f ? xlo : xhi, u2 = ux > 0.0f ? xhi : xlo;
-  float v1 = vx > 0.0f ? xlo : xhi, v2 = vx > 0.0f ? xhi : xlo;
-  float Hu = copysignf(b.H, uy), Hv = copysignf(b.H, vy);
-  // edges p0->p1 (+2u), p1->p2 (+2v), p2->p3 == -(p3->p2, +2u), p3->p0 == -(p0->p3, +2v)
-  float su = rect_edge(p0x, p0y, ux, uy, rux, ruy, u1, u2, Hu) - rect_edge(p3x, p3y, ux, uy, rux, ruy, u1, u2, Hu);
-  float sv = rect_edge(p1x, p1y, vx, vy, rvx, rvy, v1, v2, Hv) - rect_edge(p0x, p0y, vx, vy, rvx, rvy, v1, v2, Hv);
-  return 2.0f * (su + sv);       // rect_edge used half of each edge's dy
+  const float mx = rx - ux, my = ry - uy;
+  const float p0x = mx - vx, p0y = my - vy;
+  const float p3x = mx + vx, p3y = my + vy;
+  const float p1x = fmaf(2.0f, ux, p0x), p1y = fmaf(2.0f, uy, p0y);
+  const float rc = frcp(c), rs = frcp(s);
+  const float arc = fabsf(rc), ars = fabsf(rs);
+  // direction u = (c, s): y crossings use 1/s, x crossings 1/c
+  const float hr_u = b.H * ars, wr_u = b.W * arc, xo_u = -xref * rc;
+  const float ws_u = copysignf(b.W, c);
+  // direction v = (-s, c): y crossings use 1/c, x crossings -1/s
+  const float hr_v = b.H * arc, wr_v = b.W * ars, xo_v = xref * rs;
+  const float ws_v = copysignf(b.W, -s);
+  const float Lu = a.W + a.W, Lv = a.H + a.H;
+  const float hc = 0.5f * c, hs = -0.5f * s;
+  const float a1u = xo_u - wr_u, a2u = xo_u + wr_u, x1u = -xref - ws_u, x2u = -xref + ws_u;
+  const float a1v = xo_v - wr_v, a2v = xo_v + wr_v, x1v = -xref - ws_v, x2v = -xref + ws_v;
+  // edges p0->p1 (+u), p1->p2 (+v), p2->p3 == -(p3->p2, +u), p3->p0 == -(p0->p3, +v)
+  const float iu = rect_edge(p0x, -p0y * rs, hr_u, Lu, -p0x * rc, a1u, a2u, x1u, x2u, hc)
+                 - rect_edge(p3x, -p3y * rs, hr_u, Lu, -p3x * rc, a1u, a2u, x1u, x2u, hc);
+  const float iv = rect_edge(p1x, -p1y * rc, hr_v, Lv, p1x * rs, a1v, a2v, x1v, x2v, hs)
+                 - rect_edge(p0x, -p0y * rc, hr_v, Lv, p0x * rs, a1v, a2v, x1v, x2v, hs);
+  return fmaf(s, iu, c * iv);                     // dy/dtau = s along u, c along v
 }
 
+// den is a box area or a union of two: either 0 (degenerate boxes -> overlap 0) or far above
+// the denormal range, so the plain MUFU.RCP (<= 1 ulp) replaces a guarded division.
 AIDET_HD float finish_overlap(float inter, float area_a, float area_b, int mode) {
   inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_b));
   float den = (mode == MODE_IOF) ? area_a : (area_a + area_b - inter);
-  return den > 0.0f ? fdiv(inter, den) : 0.0f;
+  return den > 0.0f ? inter * frcp(den) : 0.0f;
 }
 
-AIDET_HD float rect_overlap(const RectRow& a, const RectCol& b, int mode) {
+AIDET_HD float rect_overlap(const Rect& a, const Rect& b, int mode) {
   float dx = a.cx - b.cx, dy = a.cy - b.cy, r = a.rad + b.rad;
   if (fmaf(dx, dx, dy * dy) > r * r) return 0.0f;       // disjoint bounding circles
   return finish_overlap(rect_inter(a, b), a.area, b.area, mode);
 }
 
 // prologue math (runs once per box; double keeps sin/cos at <= 0.5 ulp)
-AIDET_HD void rect_prepare(const float* box5, RectRow* row, RectCol* col) {
-  float cx = box5[0], cy = box5[1], w = fabsf(box5[2]), h = fabsf(box5[3]);
+AIDET_HD void rect_prepare(const float* box5, Rect* out) {
+  float w = fabsf(box5[2]), h = fabsf(box5[3]);
   double th = (double)box5[4];
-  float c = (float)cos(th), s = (float)sin(th);
   float W = 0.5f * w, H = 0.5f * h;
-  float rad = sqrtf(W * W + H * H) * 1.000001f + 1e-6f;
-  if (row) { row->cx = cx; row->cy = cy; row->ux = W * c; row->uy = W * s; row->vx = -H * s; row->vy = H * c;
-             row->area = w * h; row->rad = rad; }
-  if (col) { col->cx = cx; col->cy = cy; col->c = c; col->s = s; col->W = W; col->H = H;
-             col->area = w * h; col->rad = rad; }
+  out->cx = box5[0]; out->cy = box5[1];
+  out->c = (float)cos(th); out->s = (float)sin(th);
+  out->W = W; out->H = H; out->area = w * h;
+  out->rad = sqrtf(W * W + H * H) * 1.000001f + 1e-6f;
+}
+AIDET_HD void rect_prepare(const float* box5, Rect* row, Rect* col) {
+  Rect r; rect_prepare(box5, &r);
+  if (row) *row = r;
+  if (col) *col = r;
 }
 
 // --------------------------------------------- quad ^ quad (point-OBB, general)

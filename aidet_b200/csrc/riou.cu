@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(256) riou_prepare_kernel(const float* __restri
 constexpr int kColsPerTile = 256;
 constexpr int kMaxTileRows = 64;
 
-template <class K>
+template <class K, int MODE>
 __global__ void __launch_bounds__(kColsPerTile)
 riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
-                   const typename PairOp<K>::R* __restrict__ cols, int n, int mode,
+                   const typename PairOp<K>::R* __restrict__ cols, int n,
                    float* __restrict__ out, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
                    int tiles_per_cta) {
   using P = PairOp<K>;
@@ -115,12 +115,13 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     mbar_wait(&bar[buf], (it >> 1) & 1);
     const int r0 = rt * tile_rows;
     const int nr = min(tile_rows, m - r0);
-    float* o = out + (long long)r0 * ld + col;
+    float* o = out + (long long)r0 * ld + col;       // advanced by one row per iteration
+    const S* st = &stage[buf][0];
 #pragma unroll 2
     for (int r = 0; r < nr; ++r) {
-      S s = stage[buf][r];
-      float v = P::overlap(s, me, mode);
-      if (live) __stcs(o + (long long)r * ld, v);
+      float v = P::overlap(st[r], me, MODE);
+      if (live) __stcs(o, v);
+      o += ld;
     }
     __syncthreads();      // everyone is done with stage[buf] before it is refilled
   }
@@ -164,8 +165,12 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   grid = ceil_div(n_tiles, tiles_per_cta);
   {
     ProfScope prof(PROF_RIOU, s);
-    riou_matrix_kernel<K><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, mode, out, ld, tile_rows,
-                                                              n_row_tiles, n_tiles, tiles_per_cta);
+    if (mode == MODE_IOF)
+      riou_matrix_kernel<K, MODE_IOF><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, out, ld, tile_rows,
+                                                                     n_row_tiles, n_tiles, tiles_per_cta);
+    else
+      riou_matrix_kernel<K, MODE_IOU><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, out, ld, tile_rows,
+                                                                     n_row_tiles, n_tiles, tiles_per_cta);
   }
   count_launch(3);
   AIDET_CUDA(cudaGetLastError());

@@ -273,7 +273,7 @@ static NmsLayout nms_layout(int n, int n_groups, int fmt, size_t cub_bytes) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 128); return o; };
   L.keys_in = take((size_t)n * 8); L.keys_out = take((size_t)n * 8);
   L.idx_in = take((size_t)n * 4); L.order = take((size_t)n * 4);
-  L.rows = take((size_t)n * rec); L.cols = take(fmt == 4 ? 0 : (size_t)n * rec);
+  L.rows = take((size_t)n * rec); L.cols = take(fmt == 8 ? (size_t)n * rec : 0);
   L.gbounds = take((size_t)n_groups * 8); L.prefix = take((size_t)(n_groups + 1) * 4);
   L.flags = take((size_t)n);
   L.pitch32 = 2LL * ((n + 63) / 64);
