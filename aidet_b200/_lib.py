@@ -40,6 +40,12 @@ _SIGNATURES = {
     "aidet_rroi_align_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "aidet_rroi_align_bwd_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                          C.c_int, C.c_int]),
+    "aidet_rroi_align_bwd_gather_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int,
+                                                  C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

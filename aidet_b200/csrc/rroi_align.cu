@@ -15,6 +15,9 @@
 //     share the kernel (theta = 0 reproduces v1/v2)
 //   - backward scatters with 128-bit vector reductions (red.global.add.v4.f32)
 // Bound: HBM/L2 bandwidth (no reuse of arithmetic; ~2 flop per byte read).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace aidet {
@@ -71,9 +74,9 @@ __device__ __forceinline__ void decode_roi(const float* __restrict__ r, int roi_
       roi_w = r[3] * scale; roi_h = r[4] * scale;
       if (variant == 1) { roi_w = fmaxf(roi_w, 1.f); roi_h = fmaxf(roi_h, 1.f); }
     }
-    double sn, cs;                          // once per RoI: keep sin/cos at <= 0.5 ulp
-    sincos((double)r[5], &sn, &cs);
-    g.cs = (float)cs; g.sn = (float)sn; g.xb = -0.5f * roi_w; g.yb = -0.5f * roi_h;
+    float sn, cs;                           // full-range sincosf (<= 2 ulp), not the fast intrinsic
+    sincosf(r[5], &sn, &cs);
+    g.cs = cs; g.sn = sn; g.xb = -0.5f * roi_w; g.yb = -0.5f * roi_h;
   }
   g.bin_w = roi_w / (float)pw; g.bin_h = roi_h / (float)ph;
   g.gh = sample_num > 0 ? sample_num : (int)ceilf(roi_h / (float)ph);
@@ -224,6 +227,309 @@ rroi_align_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path (VEC = 4, S = gh*gw <= kTable): the shape every AIDet config uses (7x7 or 14x14
+// bins, sample_num 2).  Same mapping as above -- one CTA per RoI, lanes = channel quads,
+// slots = bins -- but the table holds float4-index offsets (tap pixel * C/4) and weights that
+// already include 1/count, a whole number of bins per table pass, and 32-bit arithmetic only:
+// per sample a thread issues 2 LDS.128, 4 IMAD.WIDE, 4 LDG.128 (or 4 RED.128) and 16 FFMA.
+// Rejected samples keep offset -1: their loads are predicated off (no divergence), so a
+// non-finite feature value can never leak through a zero weight.
+template <bool BWD>
+__global__ void __launch_bounds__(448, 2)
+rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __restrict__ rois, int roi_fmt,
+                       const int* __restrict__ roi_level, int ph, int pw, int sample_num, int variant,
+                       float* __restrict__ io, int CL, int nslots) {
+  __shared__ RoiGeom g;
+  __shared__ __align__(16) int4 toff[kTable];      // tap offsets in bytes from the image plane (x = -1: rejected)
+  __shared__ __align__(16) float4 tw[kTable];      // tap weights, 1/count folded in
+  __shared__ int n_bad;                            // rejected samples in the current table pass
+  const int k = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    const float* r = rois + (size_t)k * roi_fmt;
+    int lvl = roi_level ? roi_level[k] : 0;
+    lvl = min(max(lvl, 0), n_levels - 1);
+    g.level = lvl; g.H = lv.H[lvl]; g.W = lv.W[lvl];
+    g.batch = (int)r[0];
+    decode_roi(r, roi_fmt, lv.scale[lvl], variant, ph, pw, sample_num, g);
+    n_bad = 0;
+  }
+  __syncthreads();
+  const int nbins = ph * pw;
+  const int S = g.gh * g.gw;
+  const int nch = C >> 2;
+  const int slot = tid / CL, cl = tid - slot * CL;
+  const bool batch_ok = g.batch >= 0 && g.batch < N;
+  float4* iok = reinterpret_cast<float4*>(io) + (size_t)k * nbins * nch;       // out (fwd) or grad_out (bwd)
+  if (S <= 0 || !batch_ok) {
+    if (!BWD) {     // empty sampling grid: v1 computes 0/0 (roi_align_kernel.cu:114), v2 writes 0
+      const float fill = (variant == 0 && batch_ok) ? __int_as_float(0x7fc00000) : 0.f;
+      float* o = reinterpret_cast<float*>(iok);
+      for (int i = tid; i < nbins * C; i += blockDim.x) o[i] = fill;
+    }
+    return;
+  }
+  // image plane of this RoI, as a byte pointer; the empty asm keeps it in registers (otherwise the
+  // compiler re-derives it from the parameter table inside the tap loop)
+  const size_t plane = (size_t)g.batch * g.H * g.W * C;
+  const char* feat = BWD ? nullptr : reinterpret_cast<const char*>(lv.feat[g.level] + plane);
+  char* grad = BWD ? reinterpret_cast<char*>(lv.grad[g.level] + plane) : nullptr;
+  asm volatile("" : "+l"(feat), "+l"(grad));
+  const float inv_count = g.inv_count;
+  const int bins_per_pass = kTable / S;                       // >= 1 (host guarantees S <= kTable)
+  const unsigned pix_bytes = (unsigned)C * 4u;
+
+  for (int bin0 = 0; bin0 < nbins; bin0 += bins_per_pass) {
+    const int nb = min(bins_per_pass, nbins - bin0);
+    const int nq = nb * S;
+    if (bin0) { __syncthreads(); if (tid == 0) n_bad = 0; __syncthreads(); }
+    for (int e = tid; e < nq; e += blockDim.x) {
+      const SampleTap t = make_sample(g, bin0 * S + e, pw);
+      const bool ok = t.off[0] >= 0;
+      if (!ok) atomicAdd(&n_bad, 1);
+      toff[e] = ok ? make_int4(t.off[0] * pix_bytes, t.off[1] * pix_bytes, t.off[2] * pix_bytes, t.off[3] * pix_bytes)
+                   : make_int4(-1, 0, 0, 0);
+      tw[e] = make_float4(t.w[0] * inv_count, t.w[1] * inv_count, t.w[2] * inv_count, t.w[3] * inv_count);
+    }
+    __syncthreads();
+    if (slot >= nslots) continue;
+    const bool all_ok = n_bad == 0;                                       // CTA-uniform
+    for (int cc = cl; cc < nch; cc += CL) {
+      const unsigned cbyte = (unsigned)cc * 16u;
+      for (int b = slot; b < nb; b += nslots) {
+        const int bin = bin0 + b;
+        const int e0 = b * S;
+        if (BWD) {
+          const float4 gv = __ldcs(iok + (size_t)bin * nch + cc);
+          char* gc = grad + cbyte;
+#pragma unroll 2
+          for (int e = e0; e < e0 + S; ++e) {
+            const int4 o = toff[e];
+            if (o.x < 0) continue;                                      // warp-uniform
+            const float4 w = tw[e];
+            vred(reinterpret_cast<float4*>(gc + (unsigned)o.x), vscale(gv, w.x));
+            vred(reinterpret_cast<float4*>(gc + (unsigned)o.y), vscale(gv, w.y));
+            vred(reinterpret_cast<float4*>(gc + (unsigned)o.z), vscale(gv, w.z));
+            vred(reinterpret_cast<float4*>(gc + (unsigned)o.w), vscale(gv, w.w));
+          }
+        } else {
+          const char* fc = feat + cbyte;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (all_ok) {                   // no rejected sample in this pass: straight-line loads, 2 samples in flight
+            int e = e0;
+#pragma unroll 1
+            for (; e + 2 <= e0 + S; e += 2) {
+              const int4 oa = toff[e], ob = toff[e + 1];
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.x));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.y));
+              const float4 a2 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.z));
+              const float4 a3 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.w));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.x));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.y));
+              const float4 b2 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.z));
+              const float4 b3 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.w));
+              const float4 wa = tw[e], wb = tw[e + 1];
+              acc = vfma(wa.x, a0, acc); acc = vfma(wa.y, a1, acc); acc = vfma(wa.z, a2, acc); acc = vfma(wa.w, a3, acc);
+              acc = vfma(wb.x, b0, acc); acc = vfma(wb.y, b1, acc); acc = vfma(wb.z, b2, acc); acc = vfma(wb.w, b3, acc);
+            }
+            for (; e < e0 + S; ++e) {
+              const int4 o = toff[e];
+              const float4 w = tw[e];
+              acc = vfma(w.x, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.x)), acc);
+              acc = vfma(w.y, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.y)), acc);
+              acc = vfma(w.z, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.z)), acc);
+              acc = vfma(w.w, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.w)), acc);
+            }
+          } else {                        // RoI hangs over the image border: rejected samples are skipped
+            for (int e = e0; e < e0 + S; ++e) {
+              const int4 o = toff[e];
+              if (o.x < 0) continue;                                    // warp-uniform; rejected taps are never read
+              const float4 w = tw[e];
+              acc = vfma(w.x, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.x)), acc);
+              acc = vfma(w.y, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.y)), acc);
+              acc = vfma(w.z, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.z)), acc);
+              acc = vfma(w.w, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.w)), acc);
+            }
+          }
+          __stcs(iok + (size_t)bin * nch + cc, acc);
+        }
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Gather (output-stationary) backward.  The scatter kernel above is bound by the SM -> L2
+// reduction path (ncu: l1tex throughput 84 %, lts red sectors 52 % of peak) and needs the
+// gradient maps zero-filled first.  Here every feature pixel is written exactly once:
+//   1. tap_gen   one thread per sample point: 4 x (pixel id, weight / count); tap id = position
+//   2. bucket    the taps by pixel, either
+//        counting : per-pixel tap counts by atomics -> exclusive scan -> scatter (fast; order of a
+//                   pixel's taps, hence the float summation order, depends on atomic timing, like the
+//                   reference's atomicAdd backward), or
+//        radix    : stable radix sort of (pixel id -> tap id) -- bit-reproducible gradients
+//   3. gather    one warp per pixel: sum_i w_i * grad_out[row_i, :] with 128-bit loads, one
+//                coalesced C*4-byte store per pixel (zeros where nothing taps) -- the zero-fill
+//                of roi_align.py:63-64 / roi_align_kernel_v2.cu:325-326 is fused away.
+// CUB (scan / radix sort) is the only library code.
+struct GatherLevels {
+  float* grad[kMaxLevels];
+  int H[kMaxLevels];
+  int W[kMaxLevels];
+  float scale[kMaxLevels];
+  unsigned first[kMaxLevels + 1];       // first global pixel id of each level; [n_levels] = total
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+rroi_tap_gen_kernel(GatherLevels lv, int n_levels, int N, const float* __restrict__ rois, int roi_fmt,
+                    const int* __restrict__ roi_level, int ph, int pw, int sample_num, int variant,
+                    uint4* __restrict__ keys, uint4* __restrict__ ids, float4* __restrict__ wts,
+                    unsigned* __restrict__ counts) {
+  __shared__ RoiGeom g;
+  const int k = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const float* r = rois + (size_t)k * roi_fmt;
+    int lvl = roi_level ? roi_level[k] : 0;
+    lvl = min(max(lvl, 0), n_levels - 1);
+    g.level = lvl; g.H = lv.H[lvl]; g.W = lv.W[lvl];
+    g.batch = (int)r[0];
+    decode_roi(r, roi_fmt, lv.scale[lvl], variant, ph, pw, sample_num, g);
+  }
+  __syncthreads();
+  const int nq = ph * pw * sample_num * sample_num;         // gh = gw = sample_num on this path
+  const unsigned none = lv.first[n_levels];                 // sentinel: behind every pixel
+  const bool batch_ok = g.batch >= 0 && g.batch < N;
+  const unsigned base = lv.first[g.level] + (unsigned)g.batch * (unsigned)(g.H * g.W);
+  const float inv_count = g.inv_count;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const SampleTap t = make_sample(g, q, pw);
+    const bool ok = batch_ok && t.off[0] >= 0;
+    const size_t e = (size_t)k * nq + q;
+    const uint4 key = ok ? make_uint4(base + t.off[0], base + t.off[1], base + t.off[2], base + t.off[3])
+                         : make_uint4(none, none, none, none);
+    keys[e] = key;
+    wts[e] = make_float4(t.w[0] * inv_count, t.w[1] * inv_count, t.w[2] * inv_count, t.w[3] * inv_count);
+    if (COUNT) {
+      if (ok) { atomicAdd(counts + key.x, 1u); atomicAdd(counts + key.y, 1u); atomicAdd(counts + key.z, 1u); atomicAdd(counts + key.w, 1u); }
+    } else {
+      const unsigned id = (unsigned)(e * 4);
+      ids[e] = make_uint4(id, id + 1, id + 2, id + 3);
+    }
+  }
+}
+
+// counting variant: slot of tap i inside its pixel's segment = begin + (remaining count - 1)
+__global__ void __launch_bounds__(256)
+rroi_tap_scatter_kernel(const unsigned* __restrict__ keys, const float* __restrict__ wts, unsigned n_taps, unsigned n_pix,
+                        unsigned taps_per_row, const unsigned* __restrict__ seg_begin, unsigned* __restrict__ counts,
+                        uint2* __restrict__ sorted) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_taps) return;
+  const unsigned key = keys[i];
+  if (key >= n_pix) return;
+  const unsigned pos = seg_begin[key] + atomicSub(counts + key, 1u) - 1u;
+  sorted[pos] = make_uint2(i / taps_per_row, __float_as_uint(wts[i]));
+}
+
+// radix variant: segment bounds from the sorted keys + (row, weight) in sorted order
+__global__ void __launch_bounds__(256)
+rroi_segments_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ ids, const float* __restrict__ wts,
+                     unsigned n_taps, unsigned n_pix, unsigned taps_per_row, unsigned* __restrict__ seg_begin,
+                     unsigned* __restrict__ seg_end, uint2* __restrict__ sorted) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_taps) return;
+  const unsigned key = keys[i];
+  if (key >= n_pix) return;
+  const unsigned id = ids[i];
+  sorted[i] = make_uint2(id / taps_per_row, __float_as_uint(wts[id]));
+  if (i == 0 || keys[i - 1] != key) seg_begin[key] = i;
+  if (i == n_taps - 1 || keys[i + 1] != key) seg_end[key] = i + 1;
+}
+
+// One warp per pixel, 8 consecutive pixels per CTA (they share most of their grad_out rows -> L1
+// hits).  The pixel's (row, weight) list is fetched 32 entries at a time with one coalesced load
+// and broadcast by shuffles; four rows (8 x LDG.128 per lane at C = 256) are in flight.
+__global__ void __launch_bounds__(256)
+rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restrict__ grad_out,
+                   const uint2* __restrict__ sorted, const unsigned* __restrict__ seg_begin,
+                   const unsigned* __restrict__ seg_end) {
+  const unsigned pix = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= lv.first[n_levels]) return;
+  int l = 0;
+#pragma unroll
+  for (int j = 1; j < kMaxLevels; ++j) if (j < n_levels && pix >= lv.first[j]) l = j;
+  const int nch = C >> 2;
+  float4* dst = reinterpret_cast<float4*>(lv.grad[l]) + (size_t)(pix - lv.first[l]) * nch;
+  const unsigned b = seg_begin[pix], e = seg_end[pix];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int cb = 0; cb < nch; cb += 64) {            // every lane runs the loop: the shuffles need the full warp
+    const int cc = cb + lane;
+    const bool one = cc < nch, two = cc + 32 < nch;
+    float4 a0 = zero, a1 = zero;
+    for (unsigned c0 = b; c0 < e; c0 += 32) {
+      const int cnt = (int)min(32u, e - c0);
+      uint2 mine = make_uint2(0u, 0u);
+      if (lane < cnt) mine = __ldg(sorted + c0 + lane);
+      int t = 0;
+      for (; t + 4 <= cnt; t += 4) {
+        float4 v[4], u[4]; float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned row = __shfl_sync(0xffffffffu, mine.x, t + j);
+          w[j] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, t + j));
+          const float4* r = grad_out + (size_t)row * nch + cc;
+          v[j] = one ? __ldg(r) : zero;
+          u[j] = two ? __ldg(r + 32) : zero;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a0 = vfma(w[j], v[j], a0); a1 = vfma(w[j], u[j], a1); }
+      }
+      for (; t < cnt; ++t) {
+        const unsigned row = __shfl_sync(0xffffffffu, mine.x, t);
+        const float w = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, t));
+        const float4* r = grad_out + (size_t)row * nch + cc;
+        if (one) a0 = vfma(w, __ldg(r), a0);
+        if (two) a1 = vfma(w, __ldg(r + 32), a1);
+      }
+    }
+    if (one) __stcs(dst + cc, a0);
+    if (two) __stcs(dst + cc + 32, a1);
+  }
+}
+
+struct GatherLayout { size_t keys_in, keys_out, ids_in, ids_out, wts, sorted, seg_begin, seg_end, cub, total; size_t cub_bytes; };
+
+static int gather_cub_bytes(size_t n_taps, size_t n_pix, int end_bit, size_t* bytes) {
+  size_t a = 0, b = 0;
+  AIDET_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned*)nullptr, (unsigned*)nullptr,
+                                             (const unsigned*)nullptr, (unsigned*)nullptr, (int)n_taps, 0, end_bit,
+                                             (cudaStream_t)0));
+  AIDET_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, b, (const unsigned*)nullptr, (unsigned*)nullptr, (int)(n_pix + 1),
+                                           (cudaStream_t)0));
+  *bytes = a > b ? a : b;
+  return AIDET_OK;
+}
+
+static GatherLayout gather_layout(size_t n_taps, size_t n_pix, size_t cub_bytes) {
+  GatherLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.keys_in = take(n_taps * 4); L.keys_out = take(n_taps * 4);
+  L.ids_in = take(n_taps * 4); L.ids_out = take(n_taps * 4);
+  L.wts = take(n_taps * 4);
+  L.sorted = take(n_taps * 8);
+  L.seg_begin = take((n_pix + 1) * 4); L.seg_end = take((n_pix + 1) * 4);
+  L.cub_bytes = cub_bytes; L.cub = take(cub_bytes);
+  L.total = off + 256;
+  return L;
+}
+
+static int bits_for(unsigned long long n) { int b = 1; while ((1ULL << b) <= n) ++b; return b; }
+
 static int check_common(const int* H, const int* W, const float* scale, int n_levels, int N, int C, const float* rois,
                         int roi_fmt, const int* roi_level, int K, int ph, int pw, int sample_num, int variant) {
   AIDET_REQUIRE(n_levels >= 1 && n_levels <= kMaxLevels, "rroi_align: n_levels must be in [1,%d], got %d", kMaxLevels, n_levels);
@@ -240,12 +546,27 @@ static int check_common(const int* H, const int* W, const float* scale, int n_le
 
 static int lanes_for(int nch) { int cl = 1; while (cl < nch && cl < 256) cl <<= 1; return cl; }
 
+// Upper bound of the sampling-grid size over all RoIs is data dependent (sample_num = 0 means
+// ceil(roi/bin) points); the fast kernel needs S <= kTable, which sample_num > 0 guarantees.
 template <bool BWD>
 static int launch(RoiLevels& lv, int n_levels, int N, int C, const float* rois, int roi_fmt, const int* roi_level, int K,
                   int ph, int pw, int sample_num, int variant, float* io, bool vec4, cudaStream_t s) {
   if (K == 0) return AIDET_OK;
   ProfScope prof(BWD ? PROF_ROI_BWD : PROF_ROI_FWD, s);
-  if (vec4) {
+  long long max_plane = 0;
+  for (int l = 0; l < n_levels; l++) max_plane = max(max_plane, (long long)lv.H[l] * lv.W[l]);
+  const bool fast = vec4 && sample_num > 0 && sample_num * sample_num <= kTable && max_plane * C * 4 < 0xffffffffLL;
+  if (fast) {
+    const int nch = C / 4;
+    const int CL = lanes_for(nch);                      // power of two >= nch, <= 256
+    const int nbins = ph * pw;
+    int nslots = max(1, min(nbins, 448 / CL));
+    const int rounds = ceil_div(nbins, nslots);
+    nslots = ceil_div(nbins, rounds);                   // same number of rounds, evenly filled slots
+    const int threads = max(ceil_div(CL * nslots, 32) * 32, 64);
+    rroi_align_fast_kernel<BWD><<<K, threads, 0, s>>>(lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, pw, sample_num,
+                                                      variant, io, CL, nslots);
+  } else if (vec4) {
     rroi_align_kernel<4, BWD><<<K, 256, 0, s>>>(lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, pw, sample_num,
                                                 variant, io, lanes_for(C / 4));
   } else {
@@ -296,6 +617,87 @@ int aidet_rroi_align_bwd_f32(const float* grad_out, float* const* grad_feat_host
   if (int rc = set_device(device)) return rc;
   return launch<true>(lv, n_levels, N, C, rois, roi_fmt, roi_level, K, ph, pw, sample_num, variant,
                       const_cast<float*>(grad_out), vec4, (cudaStream_t)stream);
+}
+
+/* The gather path needs sample_num > 0 (fixed tap count), C % 4 == 0 and 16 B aligned pointers. */
+size_t aidet_rroi_align_bwd_workspace_bytes(const int* H_host, const int* W_host, int n_levels, int N, int K, int ph,
+                                            int pw, int sample_num) {
+  if (!H_host || !W_host || n_levels < 1 || n_levels > kMaxLevels || sample_num <= 0 || K <= 0) return 0;
+  unsigned long long n_pix = 0;
+  for (int l = 0; l < n_levels; l++) n_pix += (unsigned long long)N * H_host[l] * W_host[l];
+  const unsigned long long n_taps = 4ULL * K * ph * pw * sample_num * sample_num;
+  if (n_pix >= 0x7fffffffULL || n_taps >= 0x7fffffffULL) return 0;
+  size_t cub_bytes = 0;
+  if (gather_cub_bytes((size_t)n_taps, (size_t)n_pix, bits_for(n_pix), &cub_bytes) != AIDET_OK) return 0;
+  return gather_layout((size_t)n_taps, (size_t)n_pix, cub_bytes).total;
+}
+
+int aidet_rroi_align_bwd_gather_f32(const float* grad_out, float* const* grad_feat_host, const int* H_host,
+                                    const int* W_host, const float* scale_host, int n_levels, int N, int C,
+                                    const float* rois, int roi_fmt, const int* roi_level, int K, int ph, int pw,
+                                    int sample_num, int variant, int deterministic, void* workspace, size_t ws_bytes,
+                                    int device, void* stream) {
+  if (int rc = check_common(H_host, W_host, scale_host, n_levels, N, C, rois, roi_fmt, roi_level, K, ph, pw, sample_num, variant)) return rc;
+  AIDET_REQUIRE(grad_feat_host && (grad_out || K == 0), "aidet_rroi_align_bwd_gather_f32: null pointer");
+  AIDET_REQUIRE(sample_num > 0, "aidet_rroi_align_bwd_gather_f32: needs sample_num > 0 (adaptive grids use aidet_rroi_align_bwd_f32)");
+  AIDET_REQUIRE(C % 4 == 0 && (((uintptr_t)grad_out & 15) == 0), "aidet_rroi_align_bwd_gather_f32: needs C %% 4 == 0 and 16 B aligned grad_out");
+  GatherLevels lv{};
+  unsigned long long n_pix = 0;
+  for (int l = 0; l < n_levels; l++) {
+    AIDET_REQUIRE(grad_feat_host[l] && (((uintptr_t)grad_feat_host[l] & 15) == 0), "aidet_rroi_align_bwd_gather_f32: bad gradient pointer at level %d", l);
+    lv.grad[l] = grad_feat_host[l]; lv.H[l] = H_host[l]; lv.W[l] = W_host[l]; lv.scale[l] = scale_host[l];
+    lv.first[l] = (unsigned)n_pix;
+    n_pix += (unsigned long long)N * H_host[l] * W_host[l];
+  }
+  const unsigned long long n_taps = 4ULL * (unsigned long long)K * ph * pw * sample_num * sample_num;
+  AIDET_REQUIRE(n_pix < 0x7fffffffULL && n_taps < 0x7fffffffULL, "aidet_rroi_align_bwd_gather_f32: problem too large");
+  lv.first[n_levels] = (unsigned)n_pix;
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K == 0) {        // nothing taps anything: the gradient is all zeros
+    for (int l = 0; l < n_levels; l++)
+      AIDET_CUDA(cudaMemsetAsync(grad_feat_host[l], 0, (size_t)N * H_host[l] * W_host[l] * C * sizeof(float), s));
+    return AIDET_OK;
+  }
+  AIDET_REQUIRE(workspace && (((uintptr_t)workspace & 255) == 0), "aidet_rroi_align_bwd_gather_f32: workspace must be 256 B aligned");
+  const int end_bit = bits_for(n_pix);
+  size_t cub_bytes = 0;
+  if (int rc = gather_cub_bytes((size_t)n_taps, (size_t)n_pix, end_bit, &cub_bytes)) return rc;
+  const GatherLayout L = gather_layout((size_t)n_taps, (size_t)n_pix, cub_bytes);
+  if (ws_bytes < L.total) { set_error("aidet_rroi_align_bwd_gather_f32: workspace %zu < %zu", ws_bytes, L.total); return AIDET_EWORKSPACE; }
+  char* ws = (char*)workspace;
+  unsigned* keys_in = (unsigned*)(ws + L.keys_in); unsigned* keys_out = (unsigned*)(ws + L.keys_out);
+  unsigned* ids_in = (unsigned*)(ws + L.ids_in); unsigned* ids_out = (unsigned*)(ws + L.ids_out);
+  float* wts = (float*)(ws + L.wts);
+  uint2* sorted = (uint2*)(ws + L.sorted);
+  unsigned* seg_begin = (unsigned*)(ws + L.seg_begin); unsigned* seg_end = (unsigned*)(ws + L.seg_end);
+  const unsigned tpr = 4u * sample_num * sample_num;
+  const unsigned tap_blocks = (unsigned)((n_taps + 255) / 256);
+  ProfScope prof(PROF_ROI_BWD, s);
+  size_t cb = L.cub_bytes;
+  if (deterministic) {
+    AIDET_CUDA(cudaMemsetAsync(seg_begin, 0, (L.seg_end - L.seg_begin) + (size_t)(n_pix + 1) * 4, s));
+    rroi_tap_gen_kernel<false><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
+                                                 (uint4*)keys_in, (uint4*)ids_in, (float4*)wts, nullptr);
+    AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, keys_in, keys_out, ids_in, ids_out, (int)n_taps, 0, end_bit, s));
+    rroi_segments_kernel<<<tap_blocks, 256, 0, s>>>(keys_out, ids_out, wts, (unsigned)n_taps, (unsigned)n_pix, tpr,
+                                                    seg_begin, seg_end, sorted);
+    rroi_gather_kernel<<<(unsigned)((n_pix + 7) / 8), 256, 0, s>>>(lv, n_levels, C, (const float4*)grad_out, sorted,
+                                                                   seg_begin, seg_end);
+  } else {
+    unsigned* counts = seg_end;                                    // (n_pix + 1) words; the segment ends are begin[pix + 1]
+    AIDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n_pix + 1) * 4, s));
+    rroi_tap_gen_kernel<true><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
+                                                (uint4*)keys_in, nullptr, (float4*)wts, counts);
+    AIDET_CUDA(cub::DeviceScan::ExclusiveSum(ws + L.cub, cb, counts, seg_begin, (int)(n_pix + 1), s));
+    rroi_tap_scatter_kernel<<<tap_blocks, 256, 0, s>>>(keys_in, wts, (unsigned)n_taps, (unsigned)n_pix, tpr, seg_begin,
+                                                       counts, sorted);
+    rroi_gather_kernel<<<(unsigned)((n_pix + 7) / 8), 256, 0, s>>>(lv, n_levels, C, (const float4*)grad_out, sorted,
+                                                                   seg_begin, seg_begin + 1);
+  }
+  count_launch(3);
+  AIDET_CUDA(cudaGetLastError());
+  return AIDET_OK;
 }
 
 }  // extern "C"

@@ -168,3 +168,41 @@ def rroi_align_backward(grad_out_nhwc, grad_feats_nhwc, rois, scales, sample_num
         L.check(L.lib().aidet_rroi_align_bwd_f32(L.dptr(grad_out_nhwc), ptrs, Hs, Ws, sc, len(grad_feats_nhwc), N, C_,
                                                  L.dptr(rois), rois.size(1), L.dptr(lvl), K, ph, pw, int(sample_num),
                                                  int(variant), dev, L.stream_ptr(dev)), "aidet_rroi_align_bwd_f32")
+
+
+def rroi_align_backward_gather(grad_out_nhwc, grad_feats_nhwc, rois, scales, sample_num, variant, roi_level=None,
+                               workspace=None, deterministic=False):
+    """Gather backward: OVERWRITES the grad_feats_nhwc list (no zero-fill needed, no atomics on the maps).
+    deterministic=True buckets the taps with a stable radix sort (bit-reproducible gradients).
+
+    Needs sample_num > 0 and C % 4 == 0; `workspace` (uint8 CUDA tensor) is allocated when not given.
+    """
+    g0 = grad_feats_nhwc[0]
+    N, C_ = g0.size(0), g0.size(3)
+    L.require_cuda(grad_out_nhwc, "grad_output")
+    assert grad_out_nhwc.dtype == torch.float32 and grad_out_nhwc.is_contiguous()
+    K, ph, pw, C2 = grad_out_nhwc.shape
+    assert C2 == C_ and sample_num > 0 and C_ % 4 == 0
+    for t in grad_feats_nhwc:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.size(0) == N and t.size(3) == C_
+    rois = _f32c(rois, rois.size(-1), "rois")
+    lvl = None if roi_level is None else roi_level.to(device=g0.device, dtype=torch.int32).contiguous()
+    ptrs, Hs, Ws = _level_tables(grad_feats_nhwc)
+    sc = (C.c_float * len(scales))(*[float(s) for s in scales])
+    dev = g0.device.index
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        ws_ptr, ws_bytes = C.c_void_p(0), 0
+        if K > 0:
+            ws_bytes = lib.aidet_rroi_align_bwd_workspace_bytes(Hs, Ws, len(grad_feats_nhwc), N, K, ph, pw, int(sample_num))
+            if ws_bytes == 0:
+                raise RuntimeError("aidet_rroi_align_bwd_workspace_bytes: problem too large for the gather path")
+            if workspace is None or workspace.numel() < ws_bytes + 256:
+                workspace = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=g0.device)
+            ws_ptr = C.c_void_p((workspace.data_ptr() + 255) // 256 * 256)
+        L.check(lib.aidet_rroi_align_bwd_gather_f32(L.dptr(grad_out_nhwc), ptrs, Hs, Ws, sc, len(grad_feats_nhwc), N, C_,
+                                                    L.dptr(rois), rois.size(1), L.dptr(lvl), K, ph, pw,
+                                                    int(sample_num), int(variant), int(bool(deterministic)), ws_ptr,
+                                                    ws_bytes, dev,
+                                                    L.stream_ptr(dev)), "aidet_rroi_align_bwd_gather_f32")
+    return workspace

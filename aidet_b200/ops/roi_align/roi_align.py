@@ -55,8 +55,13 @@ class _RoIAlignBase(Function):
         grad_input = None
         if ctx.needs_input_grad[0]:
             go = grad_output.float().permute(0, 2, 3, 1).contiguous()
-            gf = torch.zeros((n, h, w, c), dtype=torch.float32, device=grad_output.device)
-            F.rroi_align_backward(go, [gf], rois, [ctx.spatial_scale], ctx.sample_num, ctx.variant)
+            if ctx.sample_num > 0 and c % 4 == 0:
+                # deterministic gather backward: writes every pixel once, no zero-fill, no atomics
+                gf = torch.empty((n, h, w, c), dtype=torch.float32, device=grad_output.device)
+                F.rroi_align_backward_gather(go, [gf], rois, [ctx.spatial_scale], ctx.sample_num, ctx.variant)
+            else:
+                gf = torch.zeros((n, h, w, c), dtype=torch.float32, device=grad_output.device)
+                F.rroi_align_backward(go, [gf], rois, [ctx.spatial_scale], ctx.sample_num, ctx.variant)
             grad_input = gf.permute(0, 3, 1, 2).to(grad_output.dtype)
         return grad_input
 

@@ -107,6 +107,23 @@ int aidet_rroi_align_bwd_f32(const float* grad_out, float* const* grad_feat_host
                              int ph, int pw, int sample_num, int variant,
                              int device, void* stream);
 
+/* Deterministic (atomic-free) backward: every feature pixel is written exactly once, so grad_feat
+ * need NOT be zero-filled by the caller (it is overwritten, zeros included) and the result is
+ * bit-reproducible when deterministic != 0 (stable radix sort of the taps; deterministic == 0 buckets
+ * them with atomics, faster, summation order then varies like the reference's atomicAdd backward).
+ * Same arguments as aidet_rroi_align_bwd_f32 plus a caller-owned workspace of
+ * aidet_rroi_align_bwd_workspace_bytes(...) bytes, 256 B aligned.  Requires sample_num > 0,
+ * C % 4 == 0 and 16 B aligned pointers (AIDET_EINVAL otherwise: use the scatter entry point).
+ * Replaces: roi_align_cuda.backward_v1/v2 + the zero-fill of roi_align.py:63-64 and
+ * roi_align_kernel_v2.cu:325-326. */
+size_t aidet_rroi_align_bwd_workspace_bytes(const int* H_host, const int* W_host, int n_levels, int N, int K,
+                                            int ph, int pw, int sample_num);
+int aidet_rroi_align_bwd_gather_f32(const float* grad_out, float* const* grad_feat_host, const int* H_host,
+                                    const int* W_host, const float* scale_host, int n_levels, int N, int C,
+                                    const float* rois, int roi_fmt, const int* roi_level, int K,
+                                    int ph, int pw, int sample_num, int variant, int deterministic,
+                                    void* workspace, size_t ws_bytes, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,3 +177,35 @@ def test_c3_multilevel_small(cuda):
         gref = O.roi_align_bwd(go[sel].contiguous().numpy(), tuple(feats[l].shape), rois[sel].numpy(), scales[l], 2,
                                O.ROI_V2_ALIGNED)
         _close(grads[l].cpu().numpy(), gref, "level %d bwd" % l)
+    # deterministic gather backward: overwrites (buffers start as garbage), equals the oracle, bit-reproducible
+    g1 = [torch.full_like(f, float("nan"), device=cuda) for f in feats]
+    g2 = [torch.full_like(f, 7.0, device=cuda) for f in feats]
+    g3 = [torch.full_like(f, -3.0, device=cuda) for f in feats]
+    F.rroi_align_backward_gather(go.to(cuda), g1, rois.to(cuda), scales, 2, 2, lvl.to(cuda), deterministic=True)
+    F.rroi_align_backward_gather(go.to(cuda), g2, rois.to(cuda), scales, 2, 2, lvl.to(cuda), deterministic=True)
+    F.rroi_align_backward_gather(go.to(cuda), g3, rois.to(cuda), scales, 2, 2, lvl.to(cuda), deterministic=False)
+    for l in range(4):
+        assert torch.equal(g1[l], g2[l])
+        assert torch.allclose(g1[l], g3[l], rtol=1e-5, atol=1e-5)
+        sel = (lvl == l).nonzero().flatten()
+        gref = O.roi_align_bwd(go[sel].contiguous().numpy(), tuple(feats[l].shape), rois[sel].numpy(), scales[l], 2,
+                               O.ROI_V2_ALIGNED) if sel.numel() else np.zeros(tuple(feats[l].shape))
+        _close(g1[l].cpu().numpy(), gref, "level %d gather bwd" % l)
+
+
+def test_gather_backward_edge_cases(cuda):
+    """no RoIs -> zeros; RoIs outside the image / bad batch index contribute nothing; C = 8 and C = 40 lanes."""
+    for c in (8, 40):
+        g = torch.Generator().manual_seed(c)
+        gf = [torch.full((2, 12, 12, c), float("nan"), device=cuda)]
+        F.rroi_align_backward_gather(torch.zeros((0, 3, 3, c), device=cuda), gf, torch.zeros((0, 6), device=cuda), [0.25], 2, 2)
+        assert (gf[0] == 0).all()
+        rois = torch.tensor([[0, 20.0, 20.0, 30.0, 16.0, 0.4], [1, 500.0, 500.0, 20.0, 20.0, 0.1],
+                             [5, 20.0, 20.0, 10.0, 10.0, 0.0], [1, -4.0, 10.0, 30.0, 30.0, 1.2]])
+        go = torch.randn(4, 3, 3, c, generator=g)
+        for det in (False, True):
+            gf = [torch.full((2, 12, 12, c), float("nan"), device=cuda)]
+            F.rroi_align_backward_gather(go.to(cuda), gf, rois.to(cuda), [0.25], 2, 2, deterministic=det)
+        ok = rois[:, 0] < 2
+        gref = O.roi_align_bwd(go[ok].contiguous().numpy(), (2, 12, 12, c), rois[ok].numpy(), 0.25, 2, O.ROI_V2_ALIGNED)
+        _close(gf[0].cpu().numpy(), gref, "gather edge C=%d" % c)
