@@ -236,15 +236,16 @@ rroi_align_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __restr
 // Rejected samples keep offset -1: their loads are predicated off (no divergence), so a
 // non-finite feature value can never leak through a zero weight.
 template <bool BWD>
-__global__ void __launch_bounds__(448, 2)
+__global__ void __launch_bounds__(256)
 rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __restrict__ rois, int roi_fmt,
                        const int* __restrict__ roi_level, int ph, int pw, int sample_num, int variant,
-                       float* __restrict__ io, int CL, int nslots) {
+                       float* __restrict__ io, int CL, int nslots, int groups_per_roi, int bins_per_group) {
   __shared__ RoiGeom g;
   __shared__ __align__(16) int4 toff[kTable];      // tap offsets in bytes from the image plane (x = -1: rejected)
   __shared__ __align__(16) float4 tw[kTable];      // tap weights, 1/count folded in
   __shared__ int n_bad;                            // rejected samples in the current table pass
-  const int k = blockIdx.x;
+  const int k = blockIdx.x / groups_per_roi;       // the RoI's bins are split over groups_per_roi small CTAs
+  const int grp = blockIdx.x - k * groups_per_roi;
   const int tid = threadIdx.x;
   if (tid == 0) {
     const float* r = rois + (size_t)k * roi_fmt;
@@ -257,6 +258,7 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
   }
   __syncthreads();
   const int nbins = ph * pw;
+  const int bin_begin = grp * bins_per_group, bin_end = min(nbins, bin_begin + bins_per_group);
   const int S = g.gh * g.gw;
   const int nch = C >> 2;
   const int slot = tid / CL, cl = tid - slot * CL;
@@ -266,7 +268,7 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
     if (!BWD) {     // empty sampling grid: v1 computes 0/0 (roi_align_kernel.cu:114), v2 writes 0
       const float fill = (variant == 0 && batch_ok) ? __int_as_float(0x7fc00000) : 0.f;
       float* o = reinterpret_cast<float*>(iok);
-      for (int i = tid; i < nbins * C; i += blockDim.x) o[i] = fill;
+      for (int i = bin_begin * C + tid; i < bin_end * C; i += blockDim.x) o[i] = fill;
     }
     return;
   }
@@ -280,10 +282,10 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
   const int bins_per_pass = kTable / S;                       // >= 1 (host guarantees S <= kTable)
   const unsigned pix_bytes = (unsigned)C * 4u;
 
-  for (int bin0 = 0; bin0 < nbins; bin0 += bins_per_pass) {
-    const int nb = min(bins_per_pass, nbins - bin0);
+  for (int bin0 = bin_begin; bin0 < bin_end; bin0 += bins_per_pass) {
+    const int nb = min(bins_per_pass, bin_end - bin0);
     const int nq = nb * S;
-    if (bin0) { __syncthreads(); if (tid == 0) n_bad = 0; __syncthreads(); }
+    if (bin0 != bin_begin) { __syncthreads(); if (tid == 0) n_bad = 0; __syncthreads(); }
     for (int e = tid; e < nq; e += blockDim.x) {
       const SampleTap t = make_sample(g, bin0 * S + e, pw);
       const bool ok = t.off[0] >= 0;
@@ -382,7 +384,7 @@ struct GatherLevels {
   unsigned first[kMaxLevels + 1];       // first global pixel id of each level; [n_levels] = total
 };
 
-template <bool COUNT>
+template <bool COUNT, bool IDS>
 __global__ void __launch_bounds__(256)
 rroi_tap_gen_kernel(GatherLevels lv, int n_levels, int N, const float* __restrict__ rois, int roi_fmt,
                     const int* __restrict__ roi_level, int ph, int pw, int sample_num, int variant,
@@ -412,9 +414,10 @@ rroi_tap_gen_kernel(GatherLevels lv, int n_levels, int N, const float* __restric
                          : make_uint4(none, none, none, none);
     keys[e] = key;
     wts[e] = make_float4(t.w[0] * inv_count, t.w[1] * inv_count, t.w[2] * inv_count, t.w[3] * inv_count);
-    if (COUNT) {
-      if (ok) { atomicAdd(counts + key.x, 1u); atomicAdd(counts + key.y, 1u); atomicAdd(counts + key.z, 1u); atomicAdd(counts + key.w, 1u); }
-    } else {
+    if (COUNT && ok) {
+      atomicAdd(counts + key.x, 1u); atomicAdd(counts + key.y, 1u); atomicAdd(counts + key.z, 1u); atomicAdd(counts + key.w, 1u);
+    }
+    if (IDS) {
       const unsigned id = (unsigned)(e * 4);
       ids[e] = make_uint4(id, id + 1, id + 2, id + 3);
     }
@@ -434,70 +437,88 @@ rroi_tap_scatter_kernel(const unsigned* __restrict__ keys, const float* __restri
   sorted[pos] = make_uint2(i / taps_per_row, __float_as_uint(wts[i]));
 }
 
-// radix variant: segment bounds from the sorted keys + (row, weight) in sorted order
+// radix variant: the stable sort already put tap ids in (pixel, tap id) order; rejected taps sort last,
+// so position i IS the slot and seg_begin (from the same counts + scan) indexes it.
 __global__ void __launch_bounds__(256)
-rroi_segments_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ ids, const float* __restrict__ wts,
-                     unsigned n_taps, unsigned n_pix, unsigned taps_per_row, unsigned* __restrict__ seg_begin,
-                     unsigned* __restrict__ seg_end, uint2* __restrict__ sorted) {
+rroi_tap_apply_kernel(const unsigned* __restrict__ ids, const float* __restrict__ wts, unsigned n_taps,
+                      unsigned taps_per_row, uint2* __restrict__ sorted) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_taps) return;
-  const unsigned key = keys[i];
-  if (key >= n_pix) return;
   const unsigned id = ids[i];
   sorted[i] = make_uint2(id / taps_per_row, __float_as_uint(wts[id]));
-  if (i == 0 || keys[i - 1] != key) seg_begin[key] = i;
-  if (i == n_taps - 1 || keys[i + 1] != key) seg_end[key] = i + 1;
 }
 
-// One warp per pixel, 8 consecutive pixels per CTA (they share most of their grad_out rows -> L1
-// hits).  The pixel's (row, weight) list is fetched 32 entries at a time with one coalesced load
-// and broadcast by shuffles; four rows (8 x LDG.128 per lane at C = 256) are in flight.
-__global__ void __launch_bounds__(256)
+// One warp per 4 consecutive pixels.  seg_begin is a prefix array (n_pix + 1 entries), so the taps of
+// the warp's pixels are ONE contiguous run of (row, weight) pairs: a single small load for the 5 bounds,
+// one coalesced load per 32 taps (broadcast by shuffles), then four grad_out rows (8 x LDG.128 per lane
+// at C = 256) in flight; neighbouring pixels share most rows -> L1 hits.  The kernel is latency bound
+// (ncu: no memory pipe above 45 %), so CTAs are only kGatherWarps warps: a CTA slot frees as soon as its
+// few warps are done, which keeps the resident-warp count up although the tap count per pixel varies.
+constexpr int kGatherWarps = 1;
+
+__global__ void __launch_bounds__(kGatherWarps * 32, 26)
 rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restrict__ grad_out,
-                   const uint2* __restrict__ sorted, const unsigned* __restrict__ seg_begin,
-                   const unsigned* __restrict__ seg_end) {
-  const unsigned pix = blockIdx.x * 8u + (threadIdx.x >> 5);
+                   const uint2* __restrict__ sorted, const unsigned* __restrict__ seg_begin) {
+  const unsigned n_pix = lv.first[n_levels];
+  const unsigned p0 = (blockIdx.x * (unsigned)kGatherWarps + (threadIdx.x >> 5)) * 4u;
   const int lane = threadIdx.x & 31;
-  if (pix >= lv.first[n_levels]) return;
-  int l = 0;
-#pragma unroll
-  for (int j = 1; j < kMaxLevels; ++j) if (j < n_levels && pix >= lv.first[j]) l = j;
+  if (p0 >= n_pix) return;
+  const int np = (int)min(4u, n_pix - p0);
+  unsigned bnd_l = 0;
+  if (lane <= np) bnd_l = __ldg(seg_begin + p0 + lane);
+  const unsigned run_begin = __shfl_sync(0xffffffffu, bnd_l, 0), run_end = __shfl_sync(0xffffffffu, bnd_l, np);
   const int nch = C >> 2;
-  float4* dst = reinterpret_cast<float4*>(lv.grad[l]) + (size_t)(pix - lv.first[l]) * nch;
-  const unsigned b = seg_begin[pix], e = seg_end[pix];
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int cb = 0; cb < nch; cb += 64) {            // every lane runs the loop: the shuffles need the full warp
+  for (int cb = 0; cb < nch; cb += 64) {            // every lane runs the loops: the shuffles need the full warp
     const int cc = cb + lane;
     const bool one = cc < nch, two = cc + 32 < nch;
-    float4 a0 = zero, a1 = zero;
-    for (unsigned c0 = b; c0 < e; c0 += 32) {
-      const int cnt = (int)min(32u, e - c0);
-      uint2 mine = make_uint2(0u, 0u);
-      if (lane < cnt) mine = __ldg(sorted + c0 + lane);
-      int t = 0;
-      for (; t + 4 <= cnt; t += 4) {
-        float4 v[4], u[4]; float w[4];
+    unsigned chunk = run_begin;
+    uint2 mine = make_uint2(0u, 0u);
+    if (chunk + lane < run_end) mine = __ldg(sorted + chunk + lane);
+#pragma unroll 1
+    for (int j = 0; j < np; ++j) {
+      const unsigned pix = p0 + j;
+      int l = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const unsigned row = __shfl_sync(0xffffffffu, mine.x, t + j);
-          w[j] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, t + j));
-          const float4* r = grad_out + (size_t)row * nch + cc;
-          v[j] = one ? __ldg(r) : zero;
-          u[j] = two ? __ldg(r + 32) : zero;
+      for (int q = 1; q < kMaxLevels; ++q) if (q < n_levels && pix >= lv.first[q]) l = q;
+      float4* dst = reinterpret_cast<float4*>(lv.grad[l]) + (size_t)(pix - lv.first[l]) * nch;
+      float4 a0 = zero, a1 = zero;
+      unsigned t = __shfl_sync(0xffffffffu, bnd_l, j);
+      const unsigned te = __shfl_sync(0xffffffffu, bnd_l, j + 1);
+      while (t < te) {
+        if (t >= chunk + 32u) {                     // next 32 taps of the run
+          chunk = t;
+          mine = make_uint2(0u, 0u);
+          if (chunk + lane < run_end) mine = __ldg(sorted + chunk + lane);
         }
+        const int rel = (int)(t - chunk);
+        const int m = (int)min(min(4u, te - t), 32u - (unsigned)rel);
+        if (m == 4) {
+          float4 v[4], u[4]; float w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { a0 = vfma(w[j], v[j], a0); a1 = vfma(w[j], u[j], a1); }
+          for (int i = 0; i < 4; ++i) {
+            const unsigned row = __shfl_sync(0xffffffffu, mine.x, rel + i);
+            w[i] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, rel + i));
+            const float4* r = grad_out + (size_t)row * nch + cc;
+            v[i] = one ? __ldg(r) : zero;
+            u[i] = two ? __ldg(r + 32) : zero;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { a0 = vfma(w[i], v[i], a0); a1 = vfma(w[i], u[i], a1); }
+        } else {
+          for (int i = 0; i < m; ++i) {
+            const unsigned row = __shfl_sync(0xffffffffu, mine.x, rel + i);
+            const float w = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, rel + i));
+            const float4* r = grad_out + (size_t)row * nch + cc;
+            if (one) a0 = vfma(w, __ldg(r), a0);
+            if (two) a1 = vfma(w, __ldg(r + 32), a1);
+          }
+        }
+        t += (unsigned)m;
       }
-      for (; t < cnt; ++t) {
-        const unsigned row = __shfl_sync(0xffffffffu, mine.x, t);
-        const float w = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, t));
-        const float4* r = grad_out + (size_t)row * nch + cc;
-        if (one) a0 = vfma(w, __ldg(r), a0);
-        if (two) a1 = vfma(w, __ldg(r + 32), a1);
-      }
+      if (one) __stcs(dst + cc, a0);
+      if (two) __stcs(dst + cc + 32, a1);
     }
-    if (one) __stcs(dst + cc, a0);
-    if (two) __stcs(dst + cc + 32, a1);
   }
 }
 
@@ -557,15 +578,17 @@ static int launch(RoiLevels& lv, int n_levels, int N, int C, const float* rois, 
   for (int l = 0; l < n_levels; l++) max_plane = max(max_plane, (long long)lv.H[l] * lv.W[l]);
   const bool fast = vec4 && sample_num > 0 && sample_num * sample_num <= kTable && max_plane * C * 4 < 0xffffffffLL;
   if (fast) {
+    // The kernel is latency bound (ncu: no memory pipe above 65 %), so the grid is made of many small
+    // CTAs -- one bin row of one RoI, channel lanes only -- that come and go independently: a CTA slot
+    // frees as soon as its one or two warps are done and only they wait at the table barrier.
     const int nch = C / 4;
     const int CL = lanes_for(nch);                      // power of two >= nch, <= 256
-    const int nbins = ph * pw;
-    int nslots = max(1, min(nbins, 448 / CL));
-    const int rounds = ceil_div(nbins, nslots);
-    nslots = ceil_div(nbins, rounds);                   // same number of rounds, evenly filled slots
-    const int threads = max(ceil_div(CL * nslots, 32) * 32, 64);
-    rroi_align_fast_kernel<BWD><<<K, threads, 0, s>>>(lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, pw, sample_num,
-                                                      variant, io, CL, nslots);
+    const int threads = max(CL, 32);
+    const int nslots = threads / CL;                    // > 1 only when C < 128
+    const int groups_per_roi = ph, bins_per_group = pw;
+    rroi_align_fast_kernel<BWD><<<K * groups_per_roi, threads, 0, s>>>(lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, pw,
+                                                                       sample_num, variant, io, CL, nslots, groups_per_roi,
+                                                                       bins_per_group);
   } else if (vec4) {
     rroi_align_kernel<4, BWD><<<K, 256, 0, s>>>(lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, pw, sample_num,
                                                 variant, io, lanes_for(C / 4));
@@ -675,26 +698,26 @@ int aidet_rroi_align_bwd_gather_f32(const float* grad_out, float* const* grad_fe
   const unsigned tap_blocks = (unsigned)((n_taps + 255) / 256);
   ProfScope prof(PROF_ROI_BWD, s);
   size_t cb = L.cub_bytes;
+  unsigned* counts = seg_end;                                      // (n_pix + 1) words
+  AIDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n_pix + 1) * 4, s));
+  if (deterministic)
+    rroi_tap_gen_kernel<true, true><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
+                                                      (uint4*)keys_in, (uint4*)ids_in, (float4*)wts, counts);
+  else
+    rroi_tap_gen_kernel<true, false><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
+                                                       (uint4*)keys_in, nullptr, (float4*)wts, counts);
+  AIDET_CUDA(cub::DeviceScan::ExclusiveSum(ws + L.cub, cb, counts, seg_begin, (int)(n_pix + 1), s));
   if (deterministic) {
-    AIDET_CUDA(cudaMemsetAsync(seg_begin, 0, (L.seg_end - L.seg_begin) + (size_t)(n_pix + 1) * 4, s));
-    rroi_tap_gen_kernel<false><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
-                                                 (uint4*)keys_in, (uint4*)ids_in, (float4*)wts, nullptr);
+    cb = L.cub_bytes;
     AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cb, keys_in, keys_out, ids_in, ids_out, (int)n_taps, 0, end_bit, s));
-    rroi_segments_kernel<<<tap_blocks, 256, 0, s>>>(keys_out, ids_out, wts, (unsigned)n_taps, (unsigned)n_pix, tpr,
-                                                    seg_begin, seg_end, sorted);
-    rroi_gather_kernel<<<(unsigned)((n_pix + 7) / 8), 256, 0, s>>>(lv, n_levels, C, (const float4*)grad_out, sorted,
-                                                                   seg_begin, seg_end);
+    rroi_tap_apply_kernel<<<tap_blocks, 256, 0, s>>>(ids_out, wts, (unsigned)n_taps, tpr, sorted);
   } else {
-    unsigned* counts = seg_end;                                    // (n_pix + 1) words; the segment ends are begin[pix + 1]
-    AIDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n_pix + 1) * 4, s));
-    rroi_tap_gen_kernel<true><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
-                                                (uint4*)keys_in, nullptr, (float4*)wts, counts);
-    AIDET_CUDA(cub::DeviceScan::ExclusiveSum(ws + L.cub, cb, counts, seg_begin, (int)(n_pix + 1), s));
     rroi_tap_scatter_kernel<<<tap_blocks, 256, 0, s>>>(keys_in, wts, (unsigned)n_taps, (unsigned)n_pix, tpr, seg_begin,
                                                        counts, sorted);
-    rroi_gather_kernel<<<(unsigned)((n_pix + 7) / 8), 256, 0, s>>>(lv, n_levels, C, (const float4*)grad_out, sorted,
-                                                                   seg_begin, seg_begin + 1);
   }
+  const unsigned px_per_cta = 4u * kGatherWarps;
+  rroi_gather_kernel<<<(unsigned)((n_pix + px_per_cta - 1) / px_per_cta), kGatherWarps * 32, 0, s>>>(
+      lv, n_levels, C, (const float4*)grad_out, sorted, seg_begin);
   count_launch(3);
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;

@@ -459,8 +459,8 @@ def run_ours(args, D):
                        "kernel_ms": kf / max(kfc, 1)},
                "bwd": {"ms": bms, "gbs": bytes_bwd * G / (bms * 1e-3) / 1e9, "bytes": bytes_bwd,
                        "kernel_ms": kb / max(kbc, 1),
-                       "how": "gather backward (tap list + radix sort + one warp per pixel): every gradient pixel written "
-                              "once, zero-fill fused, deterministic",
+                       "how": "gather backward (tap list bucketed per pixel by counting + scan, one warp per 4 pixels): every "
+                              "gradient pixel written once, zero-fill fused, no atomics on the maps",
                        "scatter_variant_ms": sms / args.steps},
                "gpu_launches": int(fl + bl), "scaling": "weak (replicas: every rank runs the full C3 batch)",
                "workload": "C3: %d rotated RoIs (512/img x 8), 7x7, C=%d, FPN P2-P5 of a 1024 tile, NHWC fp32, "
