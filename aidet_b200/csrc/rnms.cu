@@ -66,6 +66,28 @@ __global__ void __launch_bounds__(256) nms_keys_kernel(const float* __restrict__
   flags[i] = 0;
 }
 
+// Small inputs (n <= kRankSortMax): the seven launches of the radix sort cost more than the sort
+// itself, so the sorted position of every box is computed directly by counting -- one warp per
+// box, lanes stride over all keys: rank = #{j : (key_j, j) < (key_i, i)}.  Same order as the
+// stable radix sort (ties -> ascending original index), one launch.
+constexpr int kRankSortMax = 8192;
+
+__global__ void __launch_bounds__(256) nms_rank_sort_kernel(const uint64_t* __restrict__ keys, int n,
+                                                            uint64_t* __restrict__ keys_out, int* __restrict__ order) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const uint64_t ki = keys[i];
+  int cnt = 0;
+  for (int j = lane; j < n; j += 32) {
+    const uint64_t kj = __ldg(keys + j);
+    cnt += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0) { keys_out[cnt] = ki; order[cnt] = i; }
+}
+
 // ------------------------------------------------------------------ 2. gather
 template <class O>
 __global__ void __launch_bounds__(256) nms_gather_kernel(const float* __restrict__ boxes, const uint64_t* __restrict__ keys,
@@ -89,10 +111,10 @@ __global__ void __launch_bounds__(256) nms_gather_kernel(const float* __restrict
   }
 }
 
-// tiles of 64 rows x 256 cols over the bounding rectangle of every group (tiles under the
+// tiles of tile_rows x 256 cols over the bounding rectangle of every group (tiles under the
 // diagonal are skipped by the mask kernel); prefix[g] = first tile id of group g.
 __global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __restrict__ gstart, const int* __restrict__ gend,
-                                                               int n_groups, int* prefix) {
+                                                               int n_groups, int tile_rows, int* prefix) {
   __shared__ int warp_sum[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -100,7 +122,7 @@ __global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __rest
   for (int base = 0; base < n_groups; base += 1024) {
     int g = base + threadIdx.x;
     int v = 0;
-    if (g < n_groups) { int ng = gend[g] - gstart[g]; v = ((ng + 63) / 64) * ((ng + 255) / 256); }
+    if (g < n_groups) { int ng = gend[g] - gstart[g]; v = ((ng + tile_rows - 1) / tile_rows) * ((ng + 255) / 256); }
     int x = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
@@ -123,14 +145,14 @@ __global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __rest
 }
 
 // ------------------------------------------------------------------ 3. mask
-constexpr int kTileRows = 64;
+constexpr int kTileRows = 64;      // upper bound; small problems use 32/16/8-row tiles so every SM gets several CTAs
 constexpr int kTileCols = 256;
 
 template <class O>
 __global__ void __launch_bounds__(kTileCols)
 nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
                 const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
-                int n_groups, const float* __restrict__ thr, int n_thr, int cmp_ge, float one,
+                int n_groups, const float* __restrict__ thr, int n_thr, int cmp_ge, float one, int tile_rows,
                 uint32_t* __restrict__ mask32, long long pitch32) {
   using Row = typename O::Row; using Col = typename O::Col;
   __shared__ __align__(128) Row stage[kTileRows];
@@ -147,9 +169,9 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
     const int start = gstart[g], ng = gend[g] - start;
     const int ncq = (ng + kTileCols - 1) / kTileCols;
     const int local = t - prefix[g];
-    const int r0 = (local / ncq) * kTileRows, cq0 = (local % ncq) * kTileCols;
+    const int r0 = (local / ncq) * tile_rows, cq0 = (local % ncq) * kTileCols;
     if (cq0 + kTileCols <= r0) continue;             // tile entirely left of the diagonal word (CTA-uniform)
-    const int nr = min(kTileRows, ng - r0);
+    const int nr = min(tile_rows, ng - r0);
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)(nr * (int)sizeof(Row));
       mbar_expect_tx(&bar, bytes);
@@ -157,7 +179,7 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
     }
     const float th = thr[n_thr == 1 ? 0 : g];
     const int c0 = cq0 + warp * 32;
-    const bool need = (c0 >= r0) && (c0 < ng);       // warp-uniform
+    const bool need = (c0 + 31 > r0) && (c0 < ng);   // some column of the strip follows some row of the tile (warp-uniform)
     const int j = c0 + lane;
     const bool live = j < ng;
     Col me;
@@ -187,49 +209,90 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
 }
 
 // ------------------------------------------------------------------ 4. scan
-// One warp per group.  `removed` (one bit per sorted position of the group) lives in shared
-// memory as 32-bit half-words.  Per 32-row block: the diagonal half-words are brought to
-// every lane with shuffles, the greedy chain runs redundantly in all lanes (no divergence),
-// then the mask rows of the kept boxes are OR-ed into the later half-words.
-__global__ void __launch_bounds__(32) nms_scan_kernel(const uint32_t* __restrict__ mask32, long long pitch32,
-                                                      const int* __restrict__ gstart, const int* __restrict__ gend,
-                                                      const int* __restrict__ order, uint8_t* __restrict__ flags) {
-  extern __shared__ uint32_t removed[];
-  const int g = blockIdx.x, lane = threadIdx.x;
+// One CTA (256 threads) per group walks the group's rows in score order, 32 rows (one diagonal
+// half-word) per step, entirely on the device -- the reference copies the whole mask to the host
+// and scans it there (nms_kernel.cu:105-131).  `removed` (one bit per sorted position) lives in
+// shared memory.  The mask rows of step b+1 are prefetched with cp.async (LDGSTS) into a
+// double-buffered panel (32 rows x kScanPW half-words = the next 4096 columns) while step b runs:
+//   warp 0 : greedy chain over the 32 diagonal bits (all lanes redundantly, no divergence)
+//   all    : OR the rows of the kept boxes into `removed` -- from the panel, and straight from
+//            global memory for columns beyond the panel (groups of more than 4096 boxes only)
+constexpr int kScanPW = 128;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restrict__ mask32, long long pitch32,
+                                                       const int* __restrict__ gstart, const int* __restrict__ gend,
+                                                       const int* __restrict__ order, uint8_t* __restrict__ flags,
+                                                       int removed_cap) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* removed = sm;                                   // [removed_cap]
+  uint32_t* panel = sm + removed_cap;                       // [2][32][kScanPW]
+  __shared__ uint32_t keep_word;
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int start = gstart[g], ng = gend[g] - start;
   if (ng <= 0) return;
   const int nhw = (ng + 31) >> 5;
-  for (int h = lane; h < nhw; h += 32) removed[h] = 0;
-  __syncwarp();
+  for (int h = tid; h < nhw; h += 256) removed[h] = 0;
+
+  auto fetch = [&](int b, int buf) {
+    const int pwn = min(kScanPW, nhw - b);
+    uint32_t* dst = panel + buf * (32 * kScanPW);
+    for (int idx = tid; idx < 32 * pwn; idx += 256) {
+      const int r = idx / pwn, w = idx - r * pwn;
+      const int row = b * 32 + r;
+      if (row < ng) cp_async4(dst + r * kScanPW + w, mask32 + (long long)(start + row) * pitch32 + b + w);
+      else dst[r * kScanPW + w] = 0u;
+    }
+    cp_async_commit();
+  };
+
+  fetch(0, 0);
   for (int b = 0; b < nhw; ++b) {
-    const int row = b * 32 + lane;
-    const bool valid = row < ng;
-    const uint32_t* mrow = mask32 + (long long)(start + (valid ? row : 0)) * pitch32;
-    uint32_t d = valid ? mrow[b] : 0u;
-    uint32_t cur = removed[b];
-    if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);     // positions past the group end
-    uint32_t keep = 0;
+    const int buf = b & 1;
+    if (b + 1 < nhw) { fetch(b + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                        // panel[buf] landed; removed[] of step b-1 complete
+    const uint32_t* pan = panel + buf * (32 * kScanPW);
+    if (tid < 32) {
+      const uint32_t d = pan[lane * kScanPW];               // diagonal half-word of row 32b + lane (0 past the end)
+      uint32_t cur = removed[b];
+      if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);   // positions past the group end
+      uint32_t keep = 0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      uint32_t dk = __shfl_sync(0xffffffffu, d, k);
-      if (!(cur & (1u << k))) { keep |= 1u << k; cur |= dk; }
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t dk = __shfl_sync(0xffffffffu, d, k);
+        if (!(cur & (1u << k))) { keep |= 1u << k; cur |= dk; }
+      }
+      if (lane == 0) keep_word = keep;
     }
-    if ((keep >> lane) & 1u) flags[order[start + row]] = 1;
-    // OR the rows of the kept boxes into the half-words after b (4 rows in flight per step)
-    uint32_t todo = keep;
-    while (todo) {
-      int k0 = __ffs(todo) - 1; todo &= todo - 1;
-      int k1 = todo ? __ffs(todo) - 1 : -1; if (todo) todo &= todo - 1;
-      int k2 = todo ? __ffs(todo) - 1 : -1; if (todo) todo &= todo - 1;
-      int k3 = todo ? __ffs(todo) - 1 : -1; if (todo) todo &= todo - 1;
-      const uint32_t* m0 = mask32 + (long long)(start + b * 32 + k0) * pitch32;
-      const uint32_t* m1 = mask32 + (long long)(start + b * 32 + (k1 < 0 ? k0 : k1)) * pitch32;
-      const uint32_t* m2 = mask32 + (long long)(start + b * 32 + (k2 < 0 ? k0 : k2)) * pitch32;
-      const uint32_t* m3 = mask32 + (long long)(start + b * 32 + (k3 < 0 ? k0 : k3)) * pitch32;
-      for (int h = b + 1 + lane; h < nhw; h += 32) removed[h] |= (m0[h] | m1[h]) | (m2[h] | m3[h]);
+    __syncthreads();
+    const uint32_t keep = keep_word;
+    if (tid == 0) removed[b] = keep;                        // slot b is not read again: it now holds the keep bits
+    const int pwn = min(kScanPW, nhw - b);
+    // OR the kept rows into the later half-words: 8 threads per half-word, 4 rows each, merged with atomicOr
+    for (int idx = tid; idx < (pwn - 1) * 8; idx += 256) {
+      const int w = 1 + (idx >> 3), part = idx & 7;
+      uint32_t acc = 0, todo = (keep >> (part * 4)) & 0xfu;
+      while (todo) { const int k = part * 4 + __ffs(todo) - 1; todo &= todo - 1; acc |= pan[k * kScanPW + w]; }
+      if (acc) atomicOr(removed + b + w, acc);
     }
-    __syncwarp();
+    for (int h = b + kScanPW + tid; h < nhw; h += 256) {    // beyond the panel: only for groups > 4096 boxes
+      uint32_t acc = 0, todo = keep;
+      while (todo) {
+        const int k = __ffs(todo) - 1; todo &= todo - 1;
+        acc |= mask32[(long long)(start + b * 32 + k) * pitch32 + h];
+      }
+      removed[h] |= acc;
+    }
+    __syncthreads();                                        // panel[buf] may be refilled, removed[] is final for b+1
   }
+  // removed[b] now holds the keep bits of block b: mark the kept boxes (original indices) in parallel
+  for (int i = tid; i < ng; i += 256)
+    if ((removed[i >> 5] >> (i & 31)) & 1u) flags[order[start + i]] = 1;
 }
 
 // ------------------------------------------------------------------ 5. compact
@@ -306,26 +369,40 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
 
   const int nb = ceil_div(max(n, 2 * n_groups), 256);
   nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
-  size_t cub_bytes = L.cub_bytes;
-  AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
-                                             32 + group_bits(n_groups), s));
+  if (n <= kRankSortMax) {
+    nms_rank_sort_kernel<<<ceil_div(n, 8), 256, 0, s>>>(keys_in, n, keys_out, order);
+  } else {
+    size_t cub_bytes = L.cub_bytes;
+    AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
+                                               32 + group_bits(n_groups), s));
+  }
   nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
-  nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, prefix);
+  const int sms = sm_count(device);
+  // Row-tile height: the group sizes live on the device, so estimate the tile count as if the boxes were
+  // spread evenly over the groups (upper triangle of n_groups squares of side n / n_groups) and shrink the
+  // tiles until there are ~8 CTAs per SM -- config C2 (5822 boxes, 15 classes) gets 8-row tiles.
+  int tile_rows = kTileRows;
+  {
+    const double side = (double)n / n_groups;
+    auto est_tiles = [&](int tr) { return 0.5 * n_groups * (side / tr + 1.0) * (side / kTileCols + 1.0); };
+    while (tile_rows > 8 && est_tiles(tile_rows) < 8.0 * sms) tile_rows >>= 1;
+  }
+  nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix);
   {
     ProfScope prof(PROF_NMS_MASK, s);
-    const int sms = sm_count(device);
     // upper bound of the tile count: every group padded to full tiles
-    long long max_tiles = (long long)(ceil_div(n, kTileRows) + n_groups) * (ceil_div(n, kTileCols) + 1);
+    long long max_tiles = (long long)(ceil_div(n, tile_rows) + n_groups) * (ceil_div(n, kTileCols) + 1);
     int grid = (int)min((long long)sms * 8, max(max_tiles, 1LL));
     nms_mask_kernel<O><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr,
-                                                  cmp == AIDET_CMP_GE ? 1 : 0, one, mask32, L.pitch32);
+                                                  cmp == AIDET_CMP_GE ? 1 : 0, one, tile_rows, mask32, L.pitch32);
   }
-  size_t scan_smem = (size_t)ceil_div(n, 32) * 4 + 16;
+  const int removed_cap = ceil_div(ceil_div(n, 32), 4) * 4;          // any group may hold all n boxes
+  size_t scan_smem = ((size_t)removed_cap + 2 * 32 * kScanPW) * 4;
   if (scan_smem > 48 * 1024) {
     if (scan_smem > 227 * 1024) { set_error("nms: %d boxes exceed the single-group scan capacity", n); return AIDET_EINVAL; }
     AIDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
   }
-  nms_scan_kernel<<<n_groups, 32, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags);
+  nms_scan_kernel<<<n_groups, 256, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags, removed_cap);
   nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
   count_launch(6);        // + the CUB sort passes, which are library kernels and not counted
   AIDET_CUDA(cudaGetLastError());

@@ -61,6 +61,21 @@ def riou_aligned(a, b, mode="iou"):
     return out
 
 
+_THR_CACHE = {}
+
+
+def _scalar_thr(value, device):
+    """(1,) float32 device tensor holding a threshold; cached so a call does not launch a fill kernel."""
+    key = (device.type, device.index, value)
+    t = _THR_CACHE.get(key)
+    if t is None:
+        if len(_THR_CACHE) > 256:
+            _THR_CACHE.clear()
+        t = torch.full((1,), value, dtype=torch.float32, device=device)
+        _THR_CACHE[key] = t
+    return t
+
+
 def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False):
     """Batched greedy NMS.  boxes (n,4|5|8), scores (n,), group_ids (n,) int or None.
 
@@ -91,7 +106,7 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
     elif isinstance(iou_thr, (list, tuple)):
         thr = torch.tensor(list(iou_thr), dtype=torch.float32, device=device)
     else:
-        thr = torch.full((1,), float(iou_thr), dtype=torch.float32, device=device)
+        thr = _scalar_thr(float(iou_thr), device)
     if thr.numel() not in (1, n_groups):
         raise ValueError("iou_thr must be a scalar or have n_groups=%d entries" % n_groups)
     dev = device.index
