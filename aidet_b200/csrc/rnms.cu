@@ -213,11 +213,13 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
 // half-word) per step, entirely on the device -- the reference copies the whole mask to the host
 // and scans it there (nms_kernel.cu:105-131).  `removed` (one bit per sorted position) lives in
 // shared memory.  The mask rows of step b+1 are prefetched with cp.async (LDGSTS) into a
-// double-buffered panel (32 rows x kScanPW half-words = the next 4096 columns) while step b runs:
+// double-buffered panel (32 rows x kScanPW half-words, up to the next 16384 columns) while step b runs:
 //   warp 0 : greedy chain over the 32 diagonal bits (all lanes redundantly, no divergence)
 //   all    : OR the rows of the kept boxes into `removed` -- from the panel, and straight from
-//            global memory for columns beyond the panel (groups of more than 4096 boxes only)
-constexpr int kScanPW = 128;
+//            global memory for columns beyond the panel (groups of more than 16384 boxes only)
+// Steps whose 32 rows are all suppressed already (common once a few strong boxes are kept) skip the
+// chain, the OR and the prefetch.
+constexpr int kScanPWMax = 512;    // panel width in half-words, chosen per launch: min(512, ceil(n / 32))
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -228,7 +230,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restrict__ mask32, long long pitch32,
                                                        const int* __restrict__ gstart, const int* __restrict__ gend,
                                                        const int* __restrict__ order, uint8_t* __restrict__ flags,
-                                                       int removed_cap) {
+                                                       int removed_cap, int kScanPW) {
   extern __shared__ uint32_t sm[];
   uint32_t* removed = sm;                                   // [removed_cap]
   uint32_t* panel = sm + removed_cap;                       // [2][32][kScanPW]
@@ -239,6 +241,11 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
   const int nhw = (ng + 31) >> 5;
   for (int h = tid; h < nhw; h += 256) removed[h] = 0;
 
+  auto dead = [&](int b) {                                 // all 32 rows of step b suppressed (bits are only ever added)
+    uint32_t cur = removed[b];
+    if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);
+    return cur == ~0u;
+  };
   auto fetch = [&](int b, int buf) {
     const int pwn = min(kScanPW, nhw - b);
     uint32_t* dst = panel + buf * (32 * kScanPW);
@@ -251,11 +258,20 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
     cp_async_commit();
   };
 
+  __syncthreads();
   fetch(0, 0);
   for (int b = 0; b < nhw; ++b) {
     const int buf = b & 1;
-    if (b + 1 < nhw) { fetch(b + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();                                        // panel[buf] landed; removed[] of step b-1 complete
+    // removed[] is final for step b here (trailing barrier of step b-1): a CTA-uniform decision
+    const bool skip = dead(b);
+    if (b + 1 < nhw) {
+      if (!dead(b + 1)) fetch(b + 1, buf ^ 1); else cp_async_commit();      // keep one group per step
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    if (skip) { if (tid == 0) removed[b] = 0u; __syncthreads(); continue; }  // no box of this step is kept
+    __syncthreads();                                        // panel[buf] landed
     const uint32_t* pan = panel + buf * (32 * kScanPW);
     if (tid < 32) {
       const uint32_t d = pan[lane * kScanPW];               // diagonal half-word of row 32b + lane (0 past the end)
@@ -397,12 +413,13 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
                                                   cmp == AIDET_CMP_GE ? 1 : 0, one, tile_rows, mask32, L.pitch32);
   }
   const int removed_cap = ceil_div(ceil_div(n, 32), 4) * 4;          // any group may hold all n boxes
-  size_t scan_smem = ((size_t)removed_cap + 2 * 32 * kScanPW) * 4;
+  const int scan_pw = min(kScanPWMax, max(32, ceil_div(ceil_div(n, 32), 32) * 32));
+  size_t scan_smem = ((size_t)removed_cap + 2 * 32 * scan_pw) * 4;
   if (scan_smem > 48 * 1024) {
     if (scan_smem > 227 * 1024) { set_error("nms: %d boxes exceed the single-group scan capacity", n); return AIDET_EINVAL; }
     AIDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
   }
-  nms_scan_kernel<<<n_groups, 256, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags, removed_cap);
+  nms_scan_kernel<<<n_groups, 256, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags, removed_cap, scan_pw);
   nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
   count_launch(6);        // + the CUB sort passes, which are library kernels and not counted
   AIDET_CUDA(cudaGetLastError());

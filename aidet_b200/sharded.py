@@ -1,0 +1,168 @@
+"""Multi-GPU forms of the hot path (one process per GPU, `torch.distributed`; NCCL over NVLink on B200).
+
+* `sharded_rbbox_overlaps` -- a large rotated-IoU matrix sharded by ROW over the ranks; every rank
+  writes its rows of one (m, n) buffer and the shard results are exchanged with ONE in-place
+  all-gather (BASELINE.json config C4).
+* `scene_merge_nms` -- DOTA scene merge (mmdet/datasets/dota.py:310-336, wwtool.mergebypoly_mp /
+  mergebyrec_mp): per-tile per-class NMS on the tiles a rank owns, survivors translated to scene
+  coordinates and all-gathered, then the cross-tile merge NMS sharded by CLASS with the per-class
+  thresholds of dota.py:321-324 (BASELINE.json config C5).
+
+The compute calls go through the CUDA library (`aidet_b200.ops.functional`); both functions take
+an optional compute callable so the host-side logic (partitioning, ragged gathers, ordering) can be
+exercised on CPU with the `gloo` backend by the tests, which plug the oracle in.  There is no CPU
+compute in this module.
+"""
+import torch
+import torch.distributed as dist
+
+# mmdet/datasets/dota.py:28 (CLASSES) and :321-324 (class-wise merge thresholds)
+DOTA_CLASSES = ('harbor', 'ship', 'small-vehicle', 'large-vehicle', 'storage-tank', 'plane', 'soccer-ball-field',
+                'bridge', 'baseball-diamond', 'tennis-court', 'helicopter', 'roundabout', 'swimming-pool',
+                'ground-track-field', 'basketball-court')
+DOTA_OBB_MERGE_THR = {'harbor': 0.1, 'ship': 0.05, 'small-vehicle': 0.15, 'large-vehicle': 0.5, 'storage-tank': 0.35,
+                      'plane': 0.2, 'soccer-ball-field': 0.2, 'bridge': 0.45, 'baseball-diamond': 0.2,
+                      'tennis-court': 0.1, 'helicopter': 0.1, 'roundabout': 0.15, 'swimming-pool': 0.05,
+                      'ground-track-field': 0.4, 'basketball-court': 0.2}
+DOTA_HBB_MERGE_THR = {'harbor': 0.4, 'ship': 0.4, 'small-vehicle': 0.4, 'large-vehicle': 0.5, 'storage-tank': 0.1,
+                      'plane': 0.25, 'soccer-ball-field': 0.2, 'bridge': 0.5, 'baseball-diamond': 0.15,
+                      'tennis-court': 0.2, 'helicopter': 0.2, 'roundabout': 0.15, 'swimming-pool': 0.2,
+                      'ground-track-field': 0.15, 'basketball-court': 0.2}
+
+
+def merge_thresholds(task='obb', classwise=True):
+    """(15,) thresholds in DOTA_CLASSES order; classwise=False -> 0.3 everywhere (dota.py:326-331)."""
+    table = DOTA_OBB_MERGE_THR if task == 'obb' else DOTA_HBB_MERGE_THR
+    return torch.tensor([table[c] if classwise else 0.3 for c in DOTA_CLASSES], dtype=torch.float32)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def shard_rows(m, world, rank):
+    """Equal row blocks (the last ones may be short or empty): (rows_per_rank, first row, one past last row)."""
+    rows_per = (m + world - 1) // world if m > 0 else 0
+    r0 = min(m, rank * rows_per)
+    return rows_per, r0, min(m, r0 + rows_per)
+
+
+def _riou_cuda(a, b, mode, out):
+    from .ops import functional as F
+    return F.riou_matrix(a, b, mode, out=out)
+
+
+def sharded_rbbox_overlaps(rbboxes1, rbboxes2, mode='iou', group=None, gather=True, out=None, overlaps_fn=None):
+    """Row-sharded (m, n) overlap matrix.
+
+    rbboxes1 (m, 5|8) and rbboxes2 (n, 5|8) are replicated on every rank (100k boxes = 2 MB).  Rank r
+    computes rows [r*ceil(m/G), (r+1)*ceil(m/G)) into its slice of a (G*ceil(m/G), n) buffer; with
+    gather=True one in-place all-gather makes every rank hold the whole matrix, returned as out[:m].
+    With gather=False only the local slice is valid and (rows, (r0, r1)) is returned.
+    """
+    world, rank = _world(group)
+    m, n = rbboxes1.size(0), rbboxes2.size(0)
+    rows_per, r0, r1 = shard_rows(m, world, rank)
+    fn = overlaps_fn or _riou_cuda
+    if out is None:
+        out = torch.empty((rows_per * world, n), dtype=torch.float32, device=rbboxes1.device)
+    assert out.shape == (rows_per * world, n) and out.is_contiguous()
+    mine = out[rank * rows_per:(rank + 1) * rows_per]
+    if r1 > r0 and n > 0:
+        fn(rbboxes1[r0:r1].contiguous(), rbboxes2, mode, mine[:r1 - r0])
+    if not gather:
+        return mine[:r1 - r0], (r0, r1)
+    if world > 1 and rows_per > 0 and n > 0:
+        dist.all_gather_into_tensor(out, mine, group=group)          # in place: rank r's block is already at row r*rows_per
+    return out[:m]
+
+
+def gather_ragged(t, group=None):
+    """All-gather tensors whose first dimension differs per rank: -> (cat over ranks, counts list)."""
+    world, _ = _world(group)
+    if world == 1:
+        return t, [t.size(0)]
+    cnt = torch.tensor([t.size(0)], dtype=torch.int64, device=t.device)
+    cnts = torch.empty((world,), dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    counts = [int(c) for c in cnts.tolist()]
+    mx = max(counts)
+    if mx == 0:
+        return t, counts
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.size(0)] = t
+    buf = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    return torch.cat([buf[r * mx:r * mx + counts[r]] for r in range(world)]), counts
+
+
+def translate_to_scene(boxes, origins):
+    """Tile-frame boxes -> scene frame.  boxes (k, 4|5|8), origins (k, 2) = the (x, y) of each box's tile
+    (the `x___y` suffix of the DOTA tile names, tools/dota/dota_demo.py:33)."""
+    out = boxes.clone()
+    d = boxes.size(1)
+    if d == 5:
+        out[:, 0] += origins[:, 0]
+        out[:, 1] += origins[:, 1]
+    else:                                   # 4 (x1,y1,x2,y2) or 8 (x1,y1,...,x4,y4): x at even, y at odd columns
+        out[:, 0::2] += origins[:, :1]
+        out[:, 1::2] += origins[:, 1:]
+    return out
+
+
+def _nms_cuda(boxes, scores, groups, thr, n_groups):
+    from .ops import functional as F
+    return F.nms_batched(boxes, scores, groups, thr, n_groups=n_groups, cmp_ge=False, plus_one=False)
+
+
+def scene_merge_nms(boxes, scores, labels, tile_ids, tile_origins, num_classes=15, tile_iou_thr=0.5, merge_thr=None,
+                    group=None, nms_fn=None):
+    """Per-tile NMS + cross-tile merge NMS of one scene, tiles sharded over the ranks.
+
+    boxes (n, 5|8) in TILE coordinates, scores (n,), labels (n,) in [0, num_classes), tile_ids (n,) in
+    [0, T); tile_origins (T, 2).  All inputs are replicated (every rank sees every detection -- they are
+    KBs); rank r runs the per-tile NMS of tiles t with t % G == r in one batched launch (groups =
+    tile x class), the survivors are translated to the scene frame and all-gathered, and the merge NMS
+    (groups = class, thresholds `merge_thr` (num_classes,), default dota.py:324) is sharded by class.
+    Suppression is `IoU > thr` in both stages (DOTA_devkit keeps `ovr <= thresh`).
+
+    Returns (boxes (k, d) scene frame, scores (k,), labels (k,)) -- identical on every rank, ordered by
+    (class, tile, original index) so the result does not depend on the world size.
+    """
+    world, rank = _world(group)
+    fn = nms_fn or _nms_cuda
+    dev = boxes.device
+    n_tiles = tile_origins.size(0)
+    if merge_thr is None:
+        merge_thr = merge_thresholds('obb')
+    merge_thr = merge_thr.to(device=dev, dtype=torch.float32)
+    labels = labels.long()
+    tile_ids = tile_ids.long()
+    # ---- stage 1: per-tile, per-class NMS on my tiles
+    mine = (tile_ids % world) == rank
+    idx = mine.nonzero().flatten()
+    if idx.numel():
+        g = (tile_ids[idx] * num_classes + labels[idx]).int()
+        keep = fn(boxes[idx].contiguous(), scores[idx].contiguous(), g, tile_iou_thr, n_tiles * num_classes)
+        surv = idx[keep]
+    else:
+        surv = idx
+    surv_all, _ = gather_ragged(surv, group)
+    surv_all, _ = torch.sort(surv_all)                      # original order: independent of the world size
+    sb = translate_to_scene(boxes[surv_all], tile_origins.to(dev)[tile_ids[surv_all]])
+    ss, sl = scores[surv_all], labels[surv_all]
+    # ---- stage 2: cross-tile merge, sharded by class
+    mine2 = ((sl % world) == rank).nonzero().flatten()
+    if mine2.numel():
+        keep2 = fn(sb[mine2].contiguous(), ss[mine2].contiguous(), sl[mine2].int(), merge_thr, num_classes)
+        kept = mine2[keep2]
+    else:
+        kept = mine2
+    kept_all, _ = gather_ragged(kept, group)
+    kept_all, _ = torch.sort(kept_all)
+    # class-major output (the reference writes one Task1_<class>.txt per class, dota.py:296-308)
+    order = torch.argsort(sl[kept_all], stable=True)
+    kept_all = kept_all[order]
+    return sb[kept_all], ss[kept_all], sl[kept_all]

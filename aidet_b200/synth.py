@@ -128,3 +128,38 @@ def scene_tiles(scene=4000, tile=1024, overlap=200):
     step = tile - overlap
     xs = list(range(0, scene - tile, step)) + [scene - tile]
     return [(x, y) for y in xs for x in xs]
+
+
+def scene_dets(scene=4000, tile=1024, overlap=200, dets_per_tile=2000, num_classes=15, seed=6, dup=3):
+    """Config C5: detections of one `scene` x `scene` DOTA image cut into `tile` tiles (`overlap` px overlap).
+
+    Scene-level objects (DOTA-shaped theta-OBBs, class per object) are seen by every tile that contains their
+    centre -- objects in the overlap bands therefore appear in 2-4 tiles -- and every sighting produces `dup`
+    detections jittered by ~1 px / 0.01 rad (what a detector's surviving proposals look like), so both the
+    per-tile NMS and the cross-tile merge have work.  At most `dets_per_tile` detections per tile (top score).
+
+    Returns boxes (n,5) in TILE coordinates, scores (n,), labels (n,) int64, tile_ids (n,) int64, origins (T,2).
+    """
+    g = _gen(seed)
+    origins = torch.tensor(scene_tiles(scene, tile, overlap), dtype=torch.float32)
+    n_obj = int(dets_per_tile * origins.size(0) / dup / 1.5)
+    obj, _ = dota_boxes(n_obj, side=scene, seed=seed + 500)
+    obj_label = torch.randint(0, num_classes, (n_obj,), generator=g)
+    obj_score = _uniform(g, n_obj, 0.05, 1.0).float()
+    bs, ss, ls, ts = [], [], [], []
+    for t, (x0, y0) in enumerate(origins.tolist()):
+        inside = ((obj[:, 0] >= x0) & (obj[:, 0] < x0 + tile) & (obj[:, 1] >= y0) & (obj[:, 1] < y0 + tile)).nonzero().flatten()
+        if inside.numel() == 0:
+            continue
+        rep = inside.repeat_interleave(dup)
+        b = obj[rep].clone()
+        b[:, 0] -= x0
+        b[:, 1] -= y0
+        b += torch.randn(b.shape, generator=g) * torch.tensor([1.0, 1.0, 1.0, 1.0, 0.01])
+        b[:, 2:4] = b[:, 2:4].clamp(min=2.0)
+        s = (obj_score[rep] * _uniform(g, rep.numel(), 0.7, 1.0).float()).clamp(max=1.0)
+        if s.numel() > dets_per_tile:
+            top = torch.topk(s, dets_per_tile).indices.sort().values
+            b, s, rep = b[top], s[top], rep[top]
+        bs.append(b); ss.append(s); ls.append(obj_label[rep]); ts.append(torch.full((s.numel(),), t, dtype=torch.int64))
+    return torch.cat(bs).contiguous(), torch.cat(ss).contiguous(), torch.cat(ls).contiguous(), torch.cat(ts), origins
