@@ -71,11 +71,19 @@ __global__ void __launch_bounds__(256) riou_prepare_kernel(const float* __restri
 constexpr int kColsPerTile = 256;
 constexpr int kMaxTileRows = 64;
 
-template <class K, int MODE>
+// Destination set of one launch.  n == 1: the local result matrix.  n > 1 (row-sharded multi-GPU form):
+// the SAME row block of the (m, n) buffer on every GPU of the box -- p[q] points into rank q's buffer,
+// mapped into this process through CUDA peer / symmetric memory -- so the all-gather of the shard
+// results happens tile by tile from inside the kernel as plain stores over NVLink, overlapped with the
+// clipping arithmetic, instead of as a separate collective after it.
+constexpr int kMaxPeers = 8;
+struct OutSet { float* p[kMaxPeers]; int n; };
+
+template <class K, int MODE, bool MULTI>
 __global__ void __launch_bounds__(kColsPerTile)
 riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
                    const typename PairOp<K>::R* __restrict__ cols, int n,
-                   float* __restrict__ out, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
+                   OutSet outs, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
                    int tiles_per_cta) {
   using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
@@ -115,13 +123,20 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     mbar_wait(&bar[buf], (it >> 1) & 1);
     const int r0 = rt * tile_rows;
     const int nr = min(tile_rows, m - r0);
-    float* o = out + (long long)r0 * ld + col;       // advanced by one row per iteration
+    long long off = (long long)r0 * ld + col;        // advanced by one row per iteration
     const S* st = &stage[buf][0];
 #pragma unroll 2
     for (int r = 0; r < nr; ++r) {
       float v = P::overlap(st[r], me, MODE);
-      if (live) __stcs(o, v);
-      o += ld;
+      if (live) {
+        if (MULTI) {
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q) if (q < outs.n) __stcs(outs.p[q] + off, v);
+        } else {
+          __stcs(outs.p[0] + off, v);
+        }
+      }
+      off += ld;
     }
     __syncthreads();      // everyone is done with stage[buf] before it is refilled
   }
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restri
 }
 
 template <class K>
-static int launch_matrix(const float* a, int m, const float* b, int n, int mode, float* out, long long ld,
+static int launch_matrix(const float* a, int m, const float* b, int n, int mode, const OutSet& outs, long long ld,
                          void* ws, int device, cudaStream_t s) {
   using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
@@ -165,12 +180,12 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   grid = ceil_div(n_tiles, tiles_per_cta);
   {
     ProfScope prof(PROF_RIOU, s);
-    if (mode == MODE_IOF)
-      riou_matrix_kernel<K, MODE_IOF><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, out, ld, tile_rows,
-                                                                     n_row_tiles, n_tiles, tiles_per_cta);
-    else
-      riou_matrix_kernel<K, MODE_IOU><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, out, ld, tile_rows,
-                                                                     n_row_tiles, n_tiles, tiles_per_cta);
+#define AIDET_LAUNCH_RIOU(MODE_, MULTI_)                                                                        \
+  riou_matrix_kernel<K, MODE_, MULTI_><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, outs, ld, tile_rows,     \
+                                                                      n_row_tiles, n_tiles, tiles_per_cta)
+    if (outs.n > 1) { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, true); else AIDET_LAUNCH_RIOU(MODE_IOU, true); }
+    else            { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, false); else AIDET_LAUNCH_RIOU(MODE_IOU, false); }
+#undef AIDET_LAUNCH_RIOU
   }
   count_launch(3);
   AIDET_CUDA(cudaGetLastError());
@@ -203,8 +218,36 @@ int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt,
   }
   if (int rc = set_device(device)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, out, ld_out, workspace, device, s);
-  return launch_matrix<QuadKind>(a, m, b, n, mode, out, ld_out, workspace, device, s);
+  OutSet outs{}; outs.p[0] = out; outs.n = 1;
+  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
+  return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
+}
+
+int aidet_riou_matrix_multi_f32(const float* a, int m, const float* b, int n, int fmt, int mode,
+                                float* const* outs_host, int n_outs, long long ld_out, void* workspace,
+                                size_t ws_bytes, int device, void* stream) {
+  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_matrix_multi_f32: fmt must be 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_matrix_multi_f32: bad mode %d", mode);
+  AIDET_REQUIRE(m >= 0 && n >= 0, "aidet_riou_matrix_multi_f32: negative size");
+  AIDET_REQUIRE(outs_host && n_outs >= 1 && n_outs <= kMaxPeers, "aidet_riou_matrix_multi_f32: n_outs must be in [1,%d]", kMaxPeers);
+  if (m == 0 || n == 0) return AIDET_OK;
+  AIDET_REQUIRE(a && b && workspace, "aidet_riou_matrix_multi_f32: null pointer");
+  AIDET_REQUIRE(ld_out >= n, "aidet_riou_matrix_multi_f32: ld_out %lld < n %d", ld_out, n);
+  AIDET_REQUIRE(((uintptr_t)workspace & 15) == 0, "aidet_riou_matrix_multi_f32: workspace must be 16 B aligned");
+  if (ws_bytes < aidet_riou_workspace_bytes(m, n, fmt)) {
+    set_error("aidet_riou_matrix_multi_f32: workspace %zu < %zu", ws_bytes, aidet_riou_workspace_bytes(m, n, fmt));
+    return AIDET_EWORKSPACE;
+  }
+  OutSet outs{};
+  for (int q = 0; q < n_outs; q++) {
+    AIDET_REQUIRE(outs_host[q], "aidet_riou_matrix_multi_f32: null destination %d", q);
+    outs.p[q] = outs_host[q];
+  }
+  outs.n = n_outs;
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
+  return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
 }
 
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out, int device,

@@ -43,6 +43,27 @@ def riou_matrix(a, b, mode="iou", out=None):
     return out
 
 
+def riou_matrix_multi(a, b, dst_ptrs, ld, mode="iou"):
+    """Overlap matrix of a (m,fmt) x b (n,fmt) stored to every raw device pointer in `dst_ptrs` (row stride `ld`
+    elements): the local block and the peer-mapped blocks of the other GPUs (see aidet_b200.sharded)."""
+    assert mode in ("iou", "iof")
+    fmt = a.size(-1)
+    a, b = _f32c(a, fmt, "a"), _f32c(b, fmt, "b")
+    m, n = a.size(0), b.size(0)
+    if m == 0 or n == 0:
+        return
+    dev = a.device.index
+    lib = L.lib()
+    ws_bytes = lib.aidet_riou_workspace_bytes(m, n, fmt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    ptrs = (C.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    with torch.cuda.device(dev):
+        L.check(lib.aidet_riou_matrix_multi_f32(L.dptr(a), m, L.dptr(b), n, fmt,
+                                                L.MODE_IOF if mode == "iof" else L.MODE_IOU, ptrs, len(dst_ptrs),
+                                                int(ld), L.dptr(ws), ws_bytes, dev, L.stream_ptr(dev)),
+                "aidet_riou_matrix_multi_f32")
+
+
 def riou_aligned(a, b, mode="iou"):
     assert mode in ("iou", "iof")
     fmt = a.size(-1)

@@ -79,6 +79,42 @@ def sharded_rbbox_overlaps(rbboxes1, rbboxes2, mode='iou', group=None, gather=Tr
     return out[:m]
 
 
+class SymmetricMatrix:
+    """An (m_pad, n) float32 result buffer allocated in CUDA symmetric memory on every rank of `group`, so each
+    rank can store straight into the others' copies (NVLink peer stores).  Build once, reuse across calls."""
+
+    def __init__(self, m, n, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        world, rank = _world(group)
+        self.world, self.rank, self.m, self.n = world, rank, m, n
+        self.rows_per = shard_rows(m, world, rank)[0]
+        self.tensor = symm_mem.empty((self.rows_per * world, n), dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def barrier(self):
+        self.handle.barrier()
+
+
+def sharded_rbbox_overlaps_fused(rbboxes1, rbboxes2, sym, mode='iou'):
+    """Row-sharded overlap matrix with the all-gather fused into the kernel: rank r computes its row block and
+    stores every tile to the same rows of ALL ranks' `sym` buffers (aidet_riou_matrix_multi_f32), so when the
+    kernels and the closing barrier are done every rank holds the whole matrix.  No NCCL call on the data path.
+    """
+    from .ops import functional as F
+    m, n = rbboxes1.size(0), rbboxes2.size(0)
+    assert (m, n) == (sym.m, sym.n)
+    rows_per, r0, r1 = shard_rows(m, sym.world, sym.rank)
+    sym.barrier()                    # nobody is still reading the previous result
+    if r1 > r0 and n > 0:
+        off = sym.rank * rows_per * n * 4
+        # own copy first, then the peers in ring order so the ranks do not all target the same GPU at once
+        dst = [sym.ptrs[(sym.rank + q) % sym.world] + off for q in range(sym.world)]
+        F.riou_matrix_multi(rbboxes1[r0:r1].contiguous(), rbboxes2, dst, n, mode)
+    sym.barrier()                    # every rank's stores have landed
+    return sym.tensor[:m]
+
+
 def gather_ragged(t, group=None):
     """All-gather tensors whose first dimension differs per rank: -> (cat over ranks, counts list)."""
     world, _ = _world(group)

@@ -63,6 +63,14 @@ size_t aidet_riou_workspace_bytes(int m, int n, int fmt);
 int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt, int mode,
                           float* out, long long ld_out, void* workspace, size_t ws_bytes,
                           int device, void* stream);
+/* Row-sharded multi-GPU form: the same m x n block is stored to n_outs (<= 8) destinations -- the local
+ * buffer and the matching row block of every peer GPU's buffer (peer / symmetric-memory mappings of this
+ * process; HOST array of DEVICE pointers).  The all-gather of the shard results thereby happens from
+ * inside the kernel as stores over NVLink, tile by tile, overlapped with the arithmetic.  The caller
+ * synchronises the ranks afterwards (all stores are complete when the kernel is). */
+int aidet_riou_matrix_multi_f32(const float* a, int m, const float* b, int n, int fmt, int mode,
+                                float* const* outs_host, int n_outs, long long ld_out,
+                                void* workspace, size_t ws_bytes, int device, void* stream);
 /* element-wise pairs (is_aligned=True, geometry.py:57-71): out[i] = ovr(a[i], b[i]) */
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out,
                            int device, void* stream);
