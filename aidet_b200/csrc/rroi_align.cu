@@ -91,30 +91,48 @@ __device__ __forceinline__ void decode_roi(const float* __restrict__ r, int roi_
 }
 
 // bilinear_interpolate(_gradient) border rules, roi_align_kernel.cu:17-62,143-185
-__device__ __forceinline__ SampleTap make_sample(const RoiGeom& g, int q, int pw) {
+struct SampleCell { int yl, xl, yh, xh; float ly, lx; bool ok; };
+
+__device__ __forceinline__ SampleCell sample_cell(const RoiGeom& g, float x, float y) {
+  SampleCell c;
+  c.ok = !(y < -1.0f || y > (float)g.H || x < -1.0f || x > (float)g.W);
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int yl = (int)y, xl = (int)x, yh, xh;
+  if (yl >= g.H - 1) { yh = yl = g.H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= g.W - 1) { xh = xl = g.W - 1; x = (float)xl; } else xh = xl + 1;
+  c.yl = yl; c.xl = xl; c.yh = yh; c.xh = xh; c.ly = y - yl; c.lx = x - xl;
+  return c;
+}
+
+__device__ __forceinline__ void sample_point(const RoiGeom& g, int q, int pw, float& x, float& y) {
   const int S = g.gh * g.gw;
   const int bin = q / S, rem = q - bin * S;
   const int iy = rem / g.gw, ix = rem - iy * g.gw;
   const int p_h = bin / pw, p_w = bin - p_h * pw;
   float yy = g.yb + p_h * g.bin_h + (iy + .5f) * g.bin_h / (float)g.gh;
   float xx = g.xb + p_w * g.bin_w + (ix + .5f) * g.bin_w / (float)g.gw;
-  float x = g.ox + xx * g.cs - yy * g.sn;
-  float y = g.oy + xx * g.sn + yy * g.cs;
+  x = g.ox + xx * g.cs - yy * g.sn;
+  y = g.oy + xx * g.sn + yy * g.cs;
+}
+
+__device__ __forceinline__ SampleTap cell_taps(const RoiGeom& g, const SampleCell& c) {
   SampleTap t;
-  if (y < -1.0f || y > (float)g.H || x < -1.0f || x > (float)g.W) {
+  if (!c.ok) {
     t.off[0] = -1; t.off[1] = t.off[2] = t.off[3] = 0;
     t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
     return t;
   }
-  if (y <= 0.f) y = 0.f;
-  if (x <= 0.f) x = 0.f;
-  int yl = (int)y, xl = (int)x, yh, xh;
-  if (yl >= g.H - 1) { yh = yl = g.H - 1; y = (float)yl; } else yh = yl + 1;
-  if (xl >= g.W - 1) { xh = xl = g.W - 1; x = (float)xl; } else xh = xl + 1;
-  float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
-  t.off[0] = yl * g.W + xl; t.off[1] = yl * g.W + xh; t.off[2] = yh * g.W + xl; t.off[3] = yh * g.W + xh;
-  t.w[0] = hy * hx; t.w[1] = hy * lx; t.w[2] = ly * hx; t.w[3] = ly * lx;
+  const float hy = 1.f - c.ly, hx = 1.f - c.lx;
+  t.off[0] = c.yl * g.W + c.xl; t.off[1] = c.yl * g.W + c.xh; t.off[2] = c.yh * g.W + c.xl; t.off[3] = c.yh * g.W + c.xh;
+  t.w[0] = hy * hx; t.w[1] = hy * c.lx; t.w[2] = c.ly * hx; t.w[3] = c.ly * c.lx;
   return t;
+}
+
+__device__ __forceinline__ SampleTap make_sample(const RoiGeom& g, int q, int pw) {
+  float x, y;
+  sample_point(g, q, pw, x, y);
+  return cell_taps(g, sample_cell(g, x, y));
 }
 
 template <int VEC> struct VecT;
@@ -243,8 +261,13 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
                        const int* __restrict__ roi_level, int ph, int pw, int sample_num, int variant,
                        float* __restrict__ io, int CL, int nslots, int groups_per_roi, int bins_per_group) {
   __shared__ RoiGeom g;
-  __shared__ __align__(16) int4 toff[kTable];      // tap offsets in bytes from the image plane (x = -1: rejected)
-  __shared__ __align__(16) float4 tw[kTable];      // tap weights, 1/count folded in
+  // BWD: tap offsets in bytes from the image plane (x = -1: rejected) + tap weights, 1/count folded in.
+  // FWD: ONE 16-byte record per sample (the forward is bound by the L1 data pipe, ncu r1b: 80-85 % busy,
+  // a fifth of it these table reads): x = byte offset of tap 0 | dx | dy << 1 (0xffffffff: rejected) where
+  // dx, dy in {0, 1} say whether the right / lower neighbour is a different pixel (border clamp), y = hy / count,
+  // z = ly / count, w = lx; the four weights are rebuilt in registers (5 instructions).
+  __shared__ __align__(16) int4 toff[kTable];
+  __shared__ __align__(16) float4 tw[BWD ? kTable : 1];
   __shared__ int n_bad;                            // rejected samples in the current table pass
   const int k = blockIdx.x / groups_per_roi;       // the RoI's bins are split over groups_per_roi small CTAs
   const int grp = blockIdx.x - k * groups_per_roi;
@@ -282,19 +305,30 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
   asm volatile("" : "+l"(feat), "+l"(grad));
   const float inv_count = g.inv_count;
   const int bins_per_pass = kTable / S;                       // >= 1 (host guarantees S <= kTable)
-  const unsigned pix_bytes = (unsigned)C * 4u;
+  const unsigned pix_bytes = (unsigned)C * 4u, row_bytes = pix_bytes * (unsigned)g.W;
 
   for (int bin0 = bin_begin; bin0 < bin_end; bin0 += bins_per_pass) {
     const int nb = min(bins_per_pass, bin_end - bin0);
     const int nq = nb * S;
     if (bin0 != bin_begin) { __syncthreads(); if (tid == 0) n_bad = 0; __syncthreads(); }
     for (int e = tid; e < nq; e += blockDim.x) {
-      const SampleTap t = make_sample(g, bin0 * S + e, pw);
-      const bool ok = t.off[0] >= 0;
+      float sx, sy;
+      sample_point(g, bin0 * S + e, pw, sx, sy);
+      const SampleCell c = sample_cell(g, sx, sy);
+      const bool ok = c.ok;
       if (!ok) atomicAdd(&n_bad, 1);
-      toff[e] = ok ? make_int4(t.off[0] * pix_bytes, t.off[1] * pix_bytes, t.off[2] * pix_bytes, t.off[3] * pix_bytes)
-                   : make_int4(-1, 0, 0, 0);
-      tw[e] = make_float4(t.w[0] * inv_count, t.w[1] * inv_count, t.w[2] * inv_count, t.w[3] * inv_count);
+      if (BWD) {
+        const SampleTap t = cell_taps(g, c);
+        toff[e] = ok ? make_int4(t.off[0] * pix_bytes, t.off[1] * pix_bytes, t.off[2] * pix_bytes, t.off[3] * pix_bytes)
+                     : make_int4(-1, 0, 0, 0);
+        tw[e] = make_float4(t.w[0] * inv_count, t.w[1] * inv_count, t.w[2] * inv_count, t.w[3] * inv_count);
+      } else {
+        const unsigned dx = c.xh != c.xl, dy = c.yh != c.yl;
+        toff[e] = ok ? make_int4((int)((unsigned)(c.yl * g.W + c.xl) * pix_bytes | dx | (dy << 1)),
+                                 __float_as_int((1.f - c.ly) * inv_count), __float_as_int(c.ly * inv_count),
+                                 __float_as_int(c.lx))
+                     : make_int4(-1, 0, 0, 0);
+      }
     }
     __syncthreads();
     if (slot >= nslots) continue;
@@ -320,42 +354,59 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
         } else {
           const char* fc = feat + cbyte;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          // one sample: 4 loads issued first (addresses from the packed record), then weights + 16 FFMA
+#define AIDET_TAP_ADDR(R, O1, O2, O3)                                                   \
+          const unsigned R##0 = (unsigned)R.x & ~3u;                                      \
+          const unsigned O1 = R##0 + (((unsigned)R.x & 1u) ? pix_bytes : 0u);             \
+          const unsigned O2 = R##0 + (((unsigned)R.x & 2u) ? row_bytes : 0u);             \
+          const unsigned O3 = O2 + (O1 - R##0);
+#define AIDET_TAP_FMA(R, V0, V1, V2, V3)                                                \
+          {                                                                             \
+            const float hyi = __int_as_float(R.y), lyi = __int_as_float(R.z), lx = __int_as_float(R.w), hx = 1.f - lx; \
+            acc = vfma(hyi * hx, V0, acc); acc = vfma(hyi * lx, V1, acc);                   \
+            acc = vfma(lyi * hx, V2, acc); acc = vfma(lyi * lx, V3, acc);                   \
+          }
           if (all_ok) {                   // no rejected sample in this pass: straight-line loads, 2 samples in flight
             int e = e0;
 #pragma unroll 1
             for (; e + 2 <= e0 + S; e += 2) {
-              const int4 oa = toff[e], ob = toff[e + 1];
-              const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.x));
-              const float4 a1 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.y));
-              const float4 a2 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.z));
-              const float4 a3 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)oa.w));
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.x));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.y));
-              const float4 b2 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.z));
-              const float4 b3 = __ldg(reinterpret_cast<const float4*>(fc + (unsigned)ob.w));
-              const float4 wa = tw[e], wb = tw[e + 1];
-              acc = vfma(wa.x, a0, acc); acc = vfma(wa.y, a1, acc); acc = vfma(wa.z, a2, acc); acc = vfma(wa.w, a3, acc);
-              acc = vfma(wb.x, b0, acc); acc = vfma(wb.y, b1, acc); acc = vfma(wb.z, b2, acc); acc = vfma(wb.w, b3, acc);
+              const int4 ra = toff[e], rb = toff[e + 1];
+              AIDET_TAP_ADDR(ra, oa1, oa2, oa3)
+              AIDET_TAP_ADDR(rb, ob1, ob2, ob3)
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc + ra0));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(fc + oa1));
+              const float4 a2 = __ldg(reinterpret_cast<const float4*>(fc + oa2));
+              const float4 a3 = __ldg(reinterpret_cast<const float4*>(fc + oa3));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(fc + rb0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(fc + ob1));
+              const float4 b2 = __ldg(reinterpret_cast<const float4*>(fc + ob2));
+              const float4 b3 = __ldg(reinterpret_cast<const float4*>(fc + ob3));
+              AIDET_TAP_FMA(ra, a0, a1, a2, a3)
+              AIDET_TAP_FMA(rb, b0, b1, b2, b3)
             }
             for (; e < e0 + S; ++e) {
-              const int4 o = toff[e];
-              const float4 w = tw[e];
-              acc = vfma(w.x, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.x)), acc);
-              acc = vfma(w.y, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.y)), acc);
-              acc = vfma(w.z, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.z)), acc);
-              acc = vfma(w.w, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.w)), acc);
+              const int4 ra = toff[e];
+              AIDET_TAP_ADDR(ra, oa1, oa2, oa3)
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc + ra0));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(fc + oa1));
+              const float4 a2 = __ldg(reinterpret_cast<const float4*>(fc + oa2));
+              const float4 a3 = __ldg(reinterpret_cast<const float4*>(fc + oa3));
+              AIDET_TAP_FMA(ra, a0, a1, a2, a3)
             }
           } else {                        // RoI hangs over the image border: rejected samples are skipped
             for (int e = e0; e < e0 + S; ++e) {
-              const int4 o = toff[e];
-              if (o.x < 0) continue;                                    // warp-uniform; rejected taps are never read
-              const float4 w = tw[e];
-              acc = vfma(w.x, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.x)), acc);
-              acc = vfma(w.y, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.y)), acc);
-              acc = vfma(w.z, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.z)), acc);
-              acc = vfma(w.w, __ldg(reinterpret_cast<const float4*>(fc + (unsigned)o.w)), acc);
+              const int4 ra = toff[e];
+              if (ra.x == -1) continue;                                    // warp-uniform; rejected taps are never read
+              AIDET_TAP_ADDR(ra, oa1, oa2, oa3)
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(fc + ra0));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(fc + oa1));
+              const float4 a2 = __ldg(reinterpret_cast<const float4*>(fc + oa2));
+              const float4 a3 = __ldg(reinterpret_cast<const float4*>(fc + oa3));
+              AIDET_TAP_FMA(ra, a0, a1, a2, a3)
             }
           }
+#undef AIDET_TAP_ADDR
+#undef AIDET_TAP_FMA
           __stcs(iok + (size_t)bin * nch + cc, acc);
         }
       }
@@ -403,6 +454,34 @@ __device__ __forceinline__ SampleTap make_sample_fixed(const RoiGeom& g, int bin
   t.off[0] = yl * g.W + xl; t.off[1] = yl * g.W + xh; t.off[2] = yh * g.W + xl; t.off[3] = yh * g.W + xh;
   t.w[0] = hy * hx; t.w[1] = hy * lx; t.w[2] = ly * hx; t.w[3] = ly * lx;
   return t;
+}
+
+// One tap (corner j of sample smp of `bin`) of a G x G sampling grid: pixel index in the plane (-1: rejected
+// sample) and weight -- the lane-per-tap form of make_sample_fixed.
+template <int G>
+__device__ __forceinline__ int sample_tap_fixed(const RoiGeom& g, int bin, int smp, int j, int pw, float& w) {
+  const int iy = smp / G, ix = smp - iy * G;
+  const int p_h = bin / pw, p_w = bin - p_h * pw;
+  const float yy = g.yb + p_h * g.bin_h + (iy + .5f) * g.bin_h / (float)G;
+  const float xx = g.xb + p_w * g.bin_w + (ix + .5f) * g.bin_w / (float)G;
+  const float x = g.ox + xx * g.cs - yy * g.sn;
+  const float y = g.oy + xx * g.sn + yy * g.cs;
+  const SampleCell c = sample_cell(g, x, y);
+  w = ((j & 2) ? c.ly : 1.f - c.ly) * ((j & 1) ? c.lx : 1.f - c.lx);
+  return c.ok ? ((j & 2) ? c.yh : c.yl) * g.W + ((j & 1) ? c.xh : c.xl) : -1;
+}
+
+// Sum of w over the lanes of mask m (a __match_any_sync group), in ascending lane order, for every lane at once.
+__device__ __forceinline__ float group_sum_ordered(unsigned m, float w) {
+  const int n = __reduce_max_sync(0xffffffffu, __popc(m));           // warp uniform trip count (typically 1-4)
+  float ws = 0.f;
+  for (int it = 0; it < n; ++it) {
+    const int src = m ? __ffs(m) - 1 : 0;
+    const float wj = __shfl_sync(0xffffffffu, w, src);
+    if (m) ws += wj;
+    m &= m - 1;
+  }
+  return ws;
 }
 
 // G = sample_num (1 or 2): T = 4*G*G taps per bin live in T consecutive lanes of a warp and are merged
@@ -594,6 +673,65 @@ rroi_tap_gen_kernel(GatherLevels lv, int n_levels, int N, const float* __restric
   }
 }
 
+// Same table with the taps of each bin MERGED by pixel (sample_num 1 or 2: T = 4, 16 taps per bin live in T
+// consecutive lanes).  At the FPN level a RoI is mapped to, the 2x2 samples of a bin are 1-2 px apart, so its 16
+// taps touch ~9 distinct pixels (57 % on config C3); all taps of a bin read the SAME grad_out row, so duplicates
+// collapse into one tap whose weight is the sum of theirs (in tap order: deterministic).  Dropped duplicates get
+// the `none` key like rejected samples.  Fewer taps to bucket, and the gather kernel -- bound by the L1 data
+// pipe, one 512-byte warp load per tap -- moves 43 % fewer rows.
+template <int G, bool IDS>
+__global__ void __launch_bounds__(256)
+rroi_tap_gen_merged_kernel(GatherLevels lv, int n_levels, int N, const float* __restrict__ rois, int roi_fmt,
+                           const int* __restrict__ roi_level, int ph, int pw, int variant,
+                           unsigned* __restrict__ keys, unsigned* __restrict__ ids, float* __restrict__ wts,
+                           unsigned* __restrict__ counts) {
+  constexpr int S = G * G, T = 4 * S, BPW = 32 / T;
+  const int k = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  RoiGeom g;                                        // every thread decodes the RoI (uniform)
+  {
+    const float* r = rois + (size_t)k * roi_fmt;
+    int lvl = roi_level ? __ldg(roi_level + k) : 0;
+    lvl = min(max(lvl, 0), n_levels - 1);
+    g.level = lvl; g.H = lv.H[lvl]; g.W = lv.W[lvl];
+    float rr[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rr[i] = (i < roi_fmt) ? __ldg(r + i) : 0.f;
+    g.batch = (int)rr[0];
+    decode_roi(rr, roi_fmt, lv.scale[lvl], variant, ph, pw, G, g);
+  }
+  const int nbins = ph * pw;
+  const unsigned none = lv.first[n_levels];                 // sentinel: behind every pixel
+  const bool batch_ok = g.batch >= 0 && g.batch < N;
+  const unsigned base = lv.first[g.level] + (unsigned)g.batch * (unsigned)(g.H * g.W);
+  const float inv_count = g.inv_count;
+  const int i_tap = lane & (T - 1);
+  for (int bw = warp * BPW; bw < nbins; bw += nwarps * BPW) {       // warp uniform
+    const int b = bw + lane / T;
+    const bool valid = b < nbins;
+    int off = -1; float w = 0.f;
+    if (valid && batch_ok) {
+      off = sample_tap_fixed<G>(g, b, i_tap >> 2, i_tap & 3, pw, w);
+      w = (off >= 0) ? w * inv_count : 0.f;
+    }
+    const bool tap_ok = off >= 0;
+    // equal keys <=> same pixel of the same bin; rejected / idle lanes get unique keys
+    const unsigned long long mkey = tap_ok ? (((unsigned long long)(unsigned)off << 8) | (unsigned)(lane / T))
+                                           : (0x8000000000000000ULL | (unsigned)lane);
+    const unsigned m = __match_any_sync(0xffffffffu, mkey);
+    const bool f = tap_ok && (lane == __ffs(m) - 1);
+    const float ws = group_sum_ordered(m, w);                       // duplicates summed in tap order
+    if (valid) {
+      const size_t i = ((size_t)k * nbins + b) * T + i_tap;
+      const unsigned key = f ? base + (unsigned)off : none;
+      keys[i] = key;
+      wts[i] = ws;
+      if (f) atomicAdd(counts + key, 1u);
+      if (IDS) ids[i] = (unsigned)i;
+    }
+  }
+}
+
 // counting variant: slot of tap i inside its pixel's segment = begin + (remaining count - 1)
 __global__ void __launch_bounds__(256)
 rroi_tap_scatter_kernel(const unsigned* __restrict__ keys, const float* __restrict__ wts, unsigned n_taps, unsigned n_pix,
@@ -626,14 +764,15 @@ rroi_tap_apply_kernel(const unsigned* __restrict__ ids, const float* __restrict_
 // few warps are done, which keeps the resident-warp count up although the tap count per pixel varies.
 constexpr int kGatherWarps = 1;
 
+template <int PX>
 __global__ void __launch_bounds__(kGatherWarps * 32, 26)
 rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restrict__ grad_out,
                    const uint2* __restrict__ sorted, const unsigned* __restrict__ seg_begin) {
   const unsigned n_pix = lv.first[n_levels];
-  const unsigned p0 = (blockIdx.x * (unsigned)kGatherWarps + (threadIdx.x >> 5)) * 4u;
+  const unsigned p0 = (blockIdx.x * (unsigned)kGatherWarps + (threadIdx.x >> 5)) * (unsigned)PX;
   const int lane = threadIdx.x & 31;
   if (p0 >= n_pix) return;
-  const int np = (int)min(4u, n_pix - p0);
+  const int np = (int)min((unsigned)PX, n_pix - p0);
   unsigned bnd_l = 0;
   if (lane <= np) bnd_l = __ldg(seg_begin + p0 + lane);
   const unsigned run_begin = __shfl_sync(0xffffffffu, bnd_l, 0), run_end = __shfl_sync(0xffffffffu, bnd_l, np);
@@ -663,26 +802,20 @@ rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restric
         }
         const int rel = (int)(t - chunk);
         const int m = (int)min(min(4u, te - t), 32u - (unsigned)rel);
-        if (m == 4) {
+        {                                           // up to 4 taps: all loads issued before the first FMA
           float4 v[4], u[4]; float w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const unsigned row = __shfl_sync(0xffffffffu, mine.x, rel + i);
             w[i] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, rel + i));
             const float4* r = grad_out + (size_t)row * nch + cc;
-            v[i] = one ? __ldg(r) : zero;
-            u[i] = two ? __ldg(r + 32) : zero;
+            const bool on = i < m;                   // warp uniform
+            v[i] = (on && one) ? __ldg(r) : zero;
+            u[i] = (on && two) ? __ldg(r + 32) : zero;
+            if (!on) w[i] = 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) { a0 = vfma(w[i], v[i], a0); a1 = vfma(w[i], u[i], a1); }
-        } else {
-          for (int i = 0; i < m; ++i) {
-            const unsigned row = __shfl_sync(0xffffffffu, mine.x, rel + i);
-            const float w = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, rel + i));
-            const float4* r = grad_out + (size_t)row * nch + cc;
-            if (one) a0 = vfma(w, __ldg(r), a0);
-            if (two) a1 = vfma(w, __ldg(r + 32), a1);
-          }
         }
         t += (unsigned)m;
       }
@@ -740,6 +873,9 @@ static int check_common(const int* H, const int* W, const float* scale, int n_le
 // 35 SASS instructions per entry) -> 0.307 ms vs 0.186 ms for the one-load-per-tap kernel, so it is off.
 static const bool g_roi_fwd_unmerged = [] { const char* e = getenv("AIDET_ROI_FWD_MERGED"); return !(e && e[0] == '1'); }();
 
+// test switch (AIDET_ROI_BWD_UNMERGED=1): one tap per sample corner, no per-bin merge
+static const bool g_roi_bwd_unmerged = [] { const char* e = getenv("AIDET_ROI_BWD_UNMERGED"); return e && e[0] == '1'; }();
+static const int g_gather_px = [] { const char* e = getenv("AIDET_ROI_GATHER_PX"); int v = e ? atoi(e) : 8; return (v == 4 || v == 16) ? v : 8; }();   // pixels per gather warp (tuning)
 static const int g_fwd_ring = [] { const char* e = getenv("AIDET_ROI_FWD_RING"); return e ? atoi(e) : 4; }();   // loads in flight per lane (tuning)
 
 static int lanes_for(int nch) { int cl = 1; while (cl < nch && cl < 256) cl <<= 1; return cl; }
@@ -891,7 +1027,14 @@ int aidet_rroi_align_bwd_gather_f32(const float* grad_out, float* const* grad_fe
   size_t cb = L.cub_bytes;
   unsigned* counts = seg_end;                                      // (n_pix + 1) words
   AIDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n_pix + 1) * 4, s));
-  if (deterministic)
+  if (sample_num <= 2 && !g_roi_bwd_unmerged) {
+#define AIDET_TAPGEN(G_, IDS_)                                                                                   \
+  rroi_tap_gen_merged_kernel<G_, IDS_><<<K, 128, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, variant, \
+                                                         keys_in, ids_in, wts, counts)
+    if (sample_num == 2) { if (deterministic) AIDET_TAPGEN(2, true); else AIDET_TAPGEN(2, false); }
+    else                 { if (deterministic) AIDET_TAPGEN(1, true); else AIDET_TAPGEN(1, false); }
+#undef AIDET_TAPGEN
+  } else if (deterministic)
     rroi_tap_gen_kernel<true, true><<<K, 256, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, sample_num, variant,
                                                       (uint4*)keys_in, (uint4*)ids_in, (float4*)wts, counts);
   else
@@ -906,9 +1049,12 @@ int aidet_rroi_align_bwd_gather_f32(const float* grad_out, float* const* grad_fe
     rroi_tap_scatter_kernel<<<tap_blocks, 256, 0, s>>>(keys_in, wts, (unsigned)n_taps, (unsigned)n_pix, tpr, seg_begin,
                                                        counts, sorted);
   }
-  const unsigned px_per_cta = 4u * kGatherWarps;
-  rroi_gather_kernel<<<(unsigned)((n_pix + px_per_cta - 1) / px_per_cta), kGatherWarps * 32, 0, s>>>(
-      lv, n_levels, C, (const float4*)grad_out, sorted, seg_begin);
+  const unsigned px = (unsigned)g_gather_px * kGatherWarps;
+#define AIDET_GATHER(PX_)                                                                           \
+  rroi_gather_kernel<PX_><<<(unsigned)((n_pix + px - 1) / px), kGatherWarps * 32, 0, s>>>(            \
+      lv, n_levels, C, (const float4*)grad_out, sorted, seg_begin)
+  if (g_gather_px == 8) AIDET_GATHER(8); else if (g_gather_px == 16) AIDET_GATHER(16); else AIDET_GATHER(4);
+#undef AIDET_GATHER
   count_launch(3);
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;
