@@ -11,10 +11,15 @@
 //   2. gather  sorted boxes -> prepared records (geom.cuh) + group [start,end)
 //   3. mask    upper-triangle suppression bitmask, 32-bit half-words = __ballot_sync of
 //              "IoU > thr" over 32 column boxes held in registers, row boxes staged by TMA
-//   4. scan    one warp per group walks the rows in score order (greedy), entirely on device
-//   5. compact kept flags -> ascending original indices (nms_kernel.cu:135-138 semantics)
+//   4. scan    one CTA per group walks the rows in score order (greedy), entirely on device
+//   5. compact kept flags -> ascending original indices (nms_kernel.cu:135-138 semantics), done by
+//              whichever scan CTA finishes last
+// Up to 8192 boxes (every per-image config) steps 1-2 are ONE kernel (rank by counting) and the tile
+// prefix is computed inside the mask kernel: 3 launches per call.
 // Bound: step 3, FP32 issue (same pair arithmetic as riou.cu); steps 1,2,4,5 are latency.
 #include <cub/device/device_radix_sort.cuh>
+
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -29,12 +34,26 @@ struct NmsRect {
   static constexpr int FMT = 5;
   __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { rect_prepare(p, r, c); }
   __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return rect_overlap(a, b, MODE_IOU); }
+  __device__ static __forceinline__ bool disjoint(const Row& a, const Col& b) {
+    const float dx = a.cx - b.cx, dy = a.cy - b.cy, r = a.rad + b.rad;
+    return fmaf(dx, dx, dy * dy) > r * r;
+  }
+  __device__ static __forceinline__ float inter(const Row& a, const Col& b, float) { return rect_inter(a, b); }
+  __device__ static __forceinline__ float area(const Row& a, float) { return a.area; }
+  __device__ static __forceinline__ float area_c(const Col& b, float) { return b.area; }
 };
 struct NmsQuad {
   using Row = QuadRow; using Col = QuadCol;
   static constexpr int FMT = 8;
   __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { quad_prepare(p, r, c); }
   __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return quad_overlap(a, b, MODE_IOU); }
+  __device__ static __forceinline__ bool disjoint(const Row& a, const Col& b) {
+    const float dx = a.mx - b.mx, dy = a.my - b.my, r = a.rad + b.rad;
+    return fmaf(dx, dx, dy * dy) > r * r;
+  }
+  __device__ static __forceinline__ float inter(const Row& a, const Col& b, float) { return quad_inter(a, b); }
+  __device__ static __forceinline__ float area(const Row& a, float) { return a.area; }
+  __device__ static __forceinline__ float area_c(const Col& b, float) { return b.area; }
 };
 struct NmsHbb {
   using Row = HbbBox; using Col = HbbBox;
@@ -46,7 +65,31 @@ struct NmsHbb {
   __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float one) {
     return hbb_overlap(a, b, one, MODE_IOU);
   }
+  __device__ static __forceinline__ bool disjoint(const Row&, const Col&) { return false; }
+  __device__ static __forceinline__ float inter(const Row& a, const Col& b, float one) {
+    const float w = fmaxf(fminf(a.x2, b.x2) - fmaxf(a.x1, b.x1) + one, 0.f);
+    const float h = fmaxf(fminf(a.y2, b.y2) - fmaxf(a.y1, b.y1) + one, 0.f);
+    return w * h;
+  }
+  __device__ static __forceinline__ float area(const Row& a, float one) { return (a.x2 - a.x1 + one) * (a.y2 - a.y1 + one); }
+  __device__ static __forceinline__ float area_c(const Col& b, float one) { return (b.x2 - b.x1 + one) * (b.y2 - b.y1 + one); }
 };
+
+// "IoU cmp thr" without the division: inter cmp thr * (area_a + area_b - inter).  The union is either 0
+// (both boxes degenerate: IoU is defined 0 here, NaN > thr == false in the reference's HBB kernel) or far
+// above the denormal range.  `zero_hit` = what the comparison gives for IoU == 0.
+template <class O>
+__device__ __forceinline__ bool nms_hit(const typename O::Row& a, const typename O::Col& b, float area_b, float one,
+                                        float th, bool cmp_ge, bool zero_hit) {
+  if (O::disjoint(a, b)) return zero_hit;
+  const float area_a = O::area(a, one);
+  float inter = O::inter(a, b, one);
+  if constexpr (O::FMT != 4) inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_b));
+  const float den = area_a + area_b - inter;
+  const float rhs = th * den;
+  const bool h = cmp_ge ? (inter >= rhs) : (inter > rhs);
+  return den > 0.0f ? h : zero_hit;
+}
 
 // ------------------------------------------------------------------ 1. keys
 __device__ __forceinline__ uint32_t orderable(float f) {      // ascending uint <=> ascending float
@@ -66,26 +109,87 @@ __global__ void __launch_bounds__(256) nms_keys_kernel(const float* __restrict__
   flags[i] = 0;
 }
 
-// Small inputs (n <= kRankSortMax): the seven launches of the radix sort cost more than the sort
-// itself, so the sorted position of every box is computed directly by counting -- one warp per
-// box, lanes stride over all keys: rank = #{j : (key_j, j) < (key_i, i)}.  Same order as the
-// stable radix sort (ties -> ascending original index), one launch.
-constexpr int kRankSortMax = 8192;
+// Small inputs (n <= kRankSortMax, every per-image config): the seven launches of a radix sort cost more than
+// the sort itself, so ONE kernel does keys + sort + gather + group bounds by counting.  Keys are made unique
+// -- (group, ~score, original index) packed into 64 bits -- so the sorted position of a box is simply
+// rank = #{j : key_j < key_i}: the order of the stable radix sort (ties -> ascending original index).
+// A warp ranks kRankBoxes boxes at once (every key it builds is compared against all of them) plus, for warp
+// w <= n_groups, the first position of group w (= #{key_j < w << 45}): gstart[w], and gend[w-1].  The prepared
+// record (geom.cuh) of every box goes straight to its sorted slot.
+constexpr int kRankSortMax = 8192;          // 13 index bits
+constexpr int kRankBoxes = 4;
+constexpr int kRankGroupShift = 45;         // 13 index + 32 score bits below the group
+constexpr int kRankMaxGroups = (1 << 19) - 2;
 
-__global__ void __launch_bounds__(256) nms_rank_sort_kernel(const uint64_t* __restrict__ keys, int n,
-                                                            uint64_t* __restrict__ keys_out, int* __restrict__ order) {
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  const uint64_t ki = keys[i];
-  int cnt = 0;
-  for (int j = lane; j < n; j += 32) {
-    const uint64_t kj = __ldg(keys + j);
-    cnt += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+__device__ __forceinline__ uint64_t rank_key(const float* __restrict__ scores, const int* __restrict__ groups, int j,
+                                             uint32_t n_groups) {
+  uint32_t g = groups ? (uint32_t)__ldg(groups + j) : 0u;
+  g = min(g, n_groups);                      // ids outside [0, n_groups) sort behind every group and are never scanned
+  return ((uint64_t)g << kRankGroupShift) | ((uint64_t)(~orderable(__ldg(scores + j))) << 13) | (uint64_t)j;
+}
+
+constexpr int kRankWarps = 4;               // CTA = 4 warps = 16 boxes: ~2.5 CTAs per SM at config C2
+
+template <class O>
+__global__ void __launch_bounds__(kRankWarps * 32)
+nms_rank_gather_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ groups,
+                       int n, float one, typename O::Row* rows, typename O::Col* cols, int* __restrict__ order,
+                       uint8_t* __restrict__ flags, int* gstart, int* gend, int n_groups, int* __restrict__ counters) {
+  extern __shared__ __align__(16) uint64_t skeys[];          // all n keys: loaded once per CTA with every load in flight
+  __shared__ int s_rank[kRankWarps * kRankBoxes];            // (walking global memory instead costs one L2 / DRAM latency
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;  //  per step: the warps of an SM advance in lock step)
+  const int w = blockIdx.x * kRankWarps + wl;
+  if (blockIdx.x == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;     // tile ticket, scan-done count
+  for (int j = threadIdx.x; j < n; j += kRankWarps * 32) skeys[j] = rank_key(scores, groups, j, (uint32_t)n_groups);
+  __syncthreads();
+  const int i0 = w * kRankBoxes;
+  uint64_t ki[kRankBoxes];
+#pragma unroll
+  for (int b = 0; b < kRankBoxes; ++b) ki[b] = (i0 + b < n) ? skeys[i0 + b] : 0ull;
+  const uint64_t kg = (w <= n_groups) ? ((uint64_t)w << kRankGroupShift) : 0ull;
+  int c[kRankBoxes] = {0, 0, 0, 0}, cg = 0;
+  const int n_loop = (i0 < n || w <= n_groups) ? n : 0;     // idle warps of the last CTA only wait at the barrier
+#pragma unroll 4
+  for (int j = lane; j < n_loop; j += 32) {
+    const uint64_t kj = skeys[j];
+#pragma unroll
+    for (int b = 0; b < kRankBoxes; ++b) c[b] += (kj < ki[b]) ? 1 : 0;
+    cg += (kj < kg) ? 1 : 0;
   }
 #pragma unroll
-  for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-  if (lane == 0) { keys_out[cnt] = ki; order[cnt] = i; }
+  for (int d = 16; d; d >>= 1) {
+#pragma unroll
+    for (int b = 0; b < kRankBoxes; ++b) c[b] += __shfl_xor_sync(0xffffffffu, c[b], d);
+    cg += __shfl_xor_sync(0xffffffffu, cg, d);
+  }
+  if (lane == kRankBoxes && w <= n_groups) {
+    if (w < n_groups) gstart[w] = cg;
+    if (w > 0) gend[w - 1] = cg;
+  }
+  // the CTA's ranks go through shared memory so that consecutive lanes of ONE warp prepare the records
+  // (rect_prepare evaluates sin/cos in double; a few active lanes in every warp would multiply the FP64 work)
+  if (lane < kRankBoxes) {
+    int rank = c[0];
+#pragma unroll
+    for (int b = 1; b < kRankBoxes; ++b) if (lane == b) rank = c[b];
+    s_rank[wl * kRankBoxes + lane] = rank;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRankWarps * kRankBoxes) {
+    const int i = blockIdx.x * kRankWarps * kRankBoxes + threadIdx.x;
+    if (i < n) {
+      const int rank = s_rank[threadIdx.x];
+      order[rank] = i;
+      flags[i] = 0;
+      float bx[O::FMT];
+#pragma unroll
+      for (int k = 0; k < O::FMT; k++) bx[k] = boxes[(size_t)i * O::FMT + k];
+      typename O::Row r; typename O::Col cc;
+      O::prepare(bx, one, &r, &cc);
+      rows[rank] = r;
+      if constexpr (!std::is_same<typename O::Row, typename O::Col>::value) cols[rank] = cc;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ 2. gather
@@ -141,70 +245,104 @@ __global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __rest
     if (threadIdx.x == 1023) carry = incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) prefix[n_groups] = carry;
+  if (threadIdx.x == 0) { prefix[n_groups] = carry; prefix[n_groups + 1] = 0; prefix[n_groups + 2] = 0; }   // + tile ticket, scan-done count
 }
 
 // ------------------------------------------------------------------ 3. mask
 constexpr int kTileRows = 64;      // upper bound; small problems use 32/16/8-row tiles so every SM gets several CTAs
 constexpr int kTileCols = 256;
+constexpr int kLocalGroups = 255;   // the mask kernel scans the tile counts of up to this many groups itself
 
+struct NmsTile { int start, ng, r0, cq0, nr, g; };   // nr == 0: no tile left
+
+// Tiles are handed out by a ticket counter (balanced although diagonal tiles are cheaper and groups differ in
+// size).  Thread 0 is the scheduler: while the CTA works on tile k it draws the ticket of tile k+1, skips tiles
+// left of the diagonal, and starts the TMA copy of its row records into the other staging buffer.
 template <class O>
 __global__ void __launch_bounds__(kTileCols)
 nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
                 const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
                 int n_groups, const float* __restrict__ thr, int n_thr, int cmp_ge, float one, int tile_rows,
-                uint32_t* __restrict__ mask32, long long pitch32) {
+                uint32_t* __restrict__ mask32, long long pitch32, int* __restrict__ ticket, int local_prefix) {
   using Row = typename O::Row; using Col = typename O::Col;
-  __shared__ __align__(128) Row stage[kTileRows];
-  __shared__ __align__(8) uint64_t bar;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-  __syncthreads();
+  __shared__ __align__(128) Row stage[2][kTileRows];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ NmsTile desc[2];
+  __shared__ int sprefix[kLocalGroups + 1];
+  __shared__ int swarp[8];
+  if (local_prefix) {            // n_groups <= kLocalGroups: every CTA scans the tile counts itself (saves a launch)
+    const int g = threadIdx.x;
+    int v = 0;
+    if (g < n_groups) { int ng = gend[g] - gstart[g]; v = ((ng + tile_rows - 1) / tile_rows) * ((ng + kTileCols - 1) / kTileCols); }
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    if ((threadIdx.x & 31) == 31) swarp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    int carry = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) carry += swarp[w];
+    if (g <= n_groups) sprefix[g] = x + carry - v;            // exclusive; entry n_groups = total (v = 0 there)
+    __syncthreads();
+    prefix = sprefix;
+  }
   const int total = prefix[n_groups];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t phase = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    int lo = 0, hi = n_groups;                       // last g with prefix[g] <= t
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= t) lo = mid; else hi = mid; }
-    const int g = lo;
-    const int start = gstart[g], ng = gend[g] - start;
-    const int ncq = (ng + kTileCols - 1) / kTileCols;
-    const int local = t - prefix[g];
-    const int r0 = (local / ncq) * tile_rows, cq0 = (local % ncq) * kTileCols;
-    if (cq0 + kTileCols <= r0) continue;             // tile entirely left of the diagonal word (CTA-uniform)
-    const int nr = min(tile_rows, ng - r0);
-    if (threadIdx.x == 0) {
-      uint32_t bytes = (uint32_t)(nr * (int)sizeof(Row));
-      mbar_expect_tx(&bar, bytes);
-      tma_load_1d(stage, rows + start + r0, bytes, &bar);
+  auto schedule = [&](int buf) {                       // thread 0 only
+    for (;;) {
+      const int t = atomicAdd(ticket, 1);
+      if (t >= total) { desc[buf].nr = 0; return; }
+      int lo = 0, hi = n_groups;                       // last g with prefix[g] <= t
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= t) lo = mid; else hi = mid; }
+      const int start = gstart[lo], ng = gend[lo] - start;
+      const int ncq = (ng + kTileCols - 1) / kTileCols;
+      const int local = t - prefix[lo];
+      const int r0 = (local / ncq) * tile_rows, cq0 = (local % ncq) * kTileCols;
+      if (cq0 + kTileCols <= r0) continue;             // tile entirely left of the diagonal
+      const int nr = min(tile_rows, ng - r0);
+      desc[buf] = NmsTile{start, ng, r0, cq0, nr, lo};
+      const uint32_t bytes = (uint32_t)(nr * (int)sizeof(Row));
+      mbar_expect_tx(&bar[buf], bytes);
+      tma_load_1d(&stage[buf][0], rows + start + r0, bytes, &bar[buf]);
+      return;
     }
-    const float th = thr[n_thr == 1 ? 0 : g];
-    const int c0 = cq0 + warp * 32;
-    const bool need = (c0 + 31 > r0) && (c0 < ng);   // some column of the strip follows some row of the tile (warp-uniform)
+  };
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); schedule(0); }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool ge = cmp_ge != 0;
+  for (int it = 0;; ++it) {
+    const int buf = it & 1;
+    const NmsTile d = desc[buf];
+    if (d.nr == 0) break;
+    if (threadIdx.x == 0) schedule(buf ^ 1);           // stage[buf^1] / desc[buf^1] were released by the last barrier
+    const float th = thr[n_thr == 1 ? 0 : d.g];
+    const bool zero_hit = ge ? (0.0f >= th) : (0.0f > th);
+    const int c0 = d.cq0 + warp * 32;
+    const bool need = (c0 + 31 > d.r0) && (c0 < d.ng); // some column of the strip follows some row of the tile (warp-uniform)
     const int j = c0 + lane;
-    const bool live = j < ng;
+    const bool live = j < d.ng;
     Col me;
-    if (need) me = cols[start + (live ? j : ng - 1)];
-    mbar_wait(&bar, phase); phase ^= 1;
+    float area_me = 0.f;
+    if (need) { me = cols[d.start + (live ? j : d.ng - 1)]; area_me = O::area_c(me, one); }
+    mbar_wait(&bar[buf], (it >> 1) & 1);
     if (need) {
+      const Row* st = &stage[buf][0];
       uint32_t word = 0;
-      for (int rr = 0; rr < nr; ++rr) {
-        const int i = r0 + rr;
+      for (int rr = 0; rr < d.nr; ++rr) {
+        const int i = d.r0 + rr;
         uint32_t b = 0;
-        if (i < c0 + 31) {                           // otherwise no column of this strip follows row i
-          Row s = stage[rr];
-          float ovr = O::overlap(s, me, one);
-          bool hit = cmp_ge ? (ovr >= th) : (ovr > th);
+        if (i < c0 + 31) {                             // otherwise no column of this strip follows row i
+          const bool hit = nms_hit<O>(st[rr], me, area_me, one, th, ge, zero_hit);
           b = __ballot_sync(0xffffffffu, hit && live && j > i);
         }
         if (lane == (rr & 31)) word = b;
-        if ((rr & 31) == 31 || rr == nr - 1) {
-          int row = r0 + (rr & ~31) + lane;
-          if (lane <= (rr & 31)) mask32[(long long)(start + row) * pitch32 + (c0 >> 5)] = word;
+        if ((rr & 31) == 31 || rr == d.nr - 1) {
+          const int row = d.r0 + (rr & ~31) + lane;
+          if (lane <= (rr & 31)) mask32[(long long)(d.start + row) * pitch32 + (c0 >> 5)] = word;
           word = 0;
         }
       }
     }
-    __syncthreads();                                 // stage is free again
+    __syncthreads();                                   // stage[buf] and desc[buf] are free again
   }
 }
 
@@ -230,15 +368,17 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restrict__ mask32, long long pitch32,
                                                        const int* __restrict__ gstart, const int* __restrict__ gend,
                                                        const int* __restrict__ order, uint8_t* __restrict__ flags,
-                                                       int removed_cap, int kScanPW) {
+                                                       int removed_cap, int kScanPW, int n,
+                                                       long long* __restrict__ keep_out, int* __restrict__ n_keep,
+                                                       int* __restrict__ done) {
   extern __shared__ uint32_t sm[];
   uint32_t* removed = sm;                                   // [removed_cap]
   uint32_t* panel = sm + removed_cap;                       // [2][32][kScanPW]
   __shared__ uint32_t keep_word;
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int start = gstart[g], ng = gend[g] - start;
-  if (ng <= 0) return;
   const int nhw = (ng + 31) >> 5;
+  if (ng > 0) {
   for (int h = tid; h < nhw; h += 256) removed[h] = 0;
 
   auto dead = [&](int b) {                                 // all 32 rows of step b suppressed (bits are only ever added)
@@ -309,9 +449,49 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
   // removed[b] now holds the keep bits of block b: mark the kept boxes (original indices) in parallel
   for (int i = tid; i < ng; i += 256)
     if ((removed[i >> 5] >> (i & 31)) & 1u) flags[order[start + i]] = 1;
+  }
+  // 5. compaction, by whichever CTA finishes last (saves a launch): kept flags -> ascending original indices
+  //    (nms_kernel.cu:135-138 semantics).  `done` was zeroed by an earlier kernel of the same call.
+  if (!done) return;                                        // large inputs: a separate compaction launch follows
+  __shared__ int s_last;
+  __shared__ int warp_sum[8];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // each thread owns a run of `per` (multiple of 16) flags, read 16 at a time through L2 (other CTAs wrote them)
+  const int per = ((n + 255) / 256 + 15) & ~15;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  const uint4* f4 = reinterpret_cast<const uint4*>(flags);          // workspace slot is 128 B aligned and padded
+  int cnt = 0;
+  for (int i = lo; i < hi; i += 16) {
+    const uint4 v = __ldcg(f4 + (i >> 4));
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) if (i + q < hi) cnt += (wds[q >> 2] >> (8 * (q & 3))) & 1u;
+  }
+  int x = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) warp_sum[tid >> 5] = x;
+  __syncthreads();
+  int off = x - cnt;
+  for (int w = 0; w < (tid >> 5); ++w) off += warp_sum[w];
+  for (int i = lo; i < hi; i += 16) {
+    const uint4 v = __ldcg(f4 + (i >> 4));
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (i + q < hi && ((wds[q >> 2] >> (8 * (q & 3))) & 1u)) keep_out[off++] = i + q;
+  }
+  if (tid == 255) *n_keep = off;
 }
 
-// ------------------------------------------------------------------ 5. compact
+// ------------------------------------------------------------------ 5. compact (n > kFusedCompactMax)
+constexpr int kFusedCompactMax = 16384;
+
 __global__ void __launch_bounds__(1024) nms_compact_kernel(const uint8_t* __restrict__ flags, int n,
                                                            long long* __restrict__ keep_out, int* __restrict__ n_keep) {
   __shared__ int warp_sum[32];
@@ -353,8 +533,8 @@ static NmsLayout nms_layout(int n, int n_groups, int fmt, size_t cub_bytes) {
   L.keys_in = take((size_t)n * 8); L.keys_out = take((size_t)n * 8);
   L.idx_in = take((size_t)n * 4); L.order = take((size_t)n * 4);
   L.rows = take((size_t)n * rec); L.cols = take(fmt == 8 ? (size_t)n * rec : 0);
-  L.gbounds = take((size_t)n_groups * 8); L.prefix = take((size_t)(n_groups + 1) * 4);
-  L.flags = take((size_t)n);
+  L.gbounds = take((size_t)n_groups * 8); L.prefix = take((size_t)(n_groups + 3) * 4);
+  L.flags = take((size_t)n + 16);
   L.pitch32 = 2LL * ((n + 63) / 64);
   L.mask = take((size_t)n * (size_t)L.pitch32 * 4);
   L.cub_bytes = cub_bytes; L.cub = take(cub_bytes);
@@ -383,16 +563,23 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
   uint8_t* flags = (uint8_t*)(ws + L.flags);
   uint32_t* mask32 = (uint32_t*)(ws + L.mask);
 
-  const int nb = ceil_div(max(n, 2 * n_groups), 256);
-  nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
-  if (n <= kRankSortMax) {
-    nms_rank_sort_kernel<<<ceil_div(n, 8), 256, 0, s>>>(keys_in, n, keys_out, order);
+  int* counters = prefix + n_groups + 1;                    // [0] tile ticket of the mask kernel, [1] finished scan CTAs
+  const bool small = n <= kRankSortMax && n_groups <= kRankMaxGroups;
+  if (small) {
+    const int warps = max(ceil_div(n, kRankBoxes), n_groups + 1);
+    const size_t key_smem = (size_t)n * 8;
+    if (key_smem > 48 * 1024)
+      AIDET_CUDA(cudaFuncSetAttribute(nms_rank_gather_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)key_smem));
+    nms_rank_gather_kernel<O><<<ceil_div(warps, kRankWarps), kRankWarps * 32, key_smem, s>>>(
+        boxes, scores, groups, n, one, rows, cols, order, flags, gstart, gend, n_groups, counters);
   } else {
+    const int nb = ceil_div(max(n, 2 * n_groups), 256);
+    nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
     size_t cub_bytes = L.cub_bytes;
     AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
                                                32 + group_bits(n_groups), s));
+    nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
   }
-  nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
   const int sms = sm_count(device);
   // Row-tile height: the group sizes live on the device, so estimate the tile count as if the boxes were
   // spread evenly over the groups (upper triangle of n_groups squares of side n / n_groups) and shrink the
@@ -403,25 +590,30 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     auto est_tiles = [&](int tr) { return 0.5 * n_groups * (side / tr + 1.0) * (side / kTileCols + 1.0); };
     while (tile_rows > 8 && est_tiles(tile_rows) < 8.0 * sms) tile_rows >>= 1;
   }
-  nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix);
+  const int local_prefix = (small && n_groups <= kLocalGroups) ? 1 : 0;
+  if (!local_prefix) nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix);
   {
     ProfScope prof(PROF_NMS_MASK, s);
     // upper bound of the tile count: every group padded to full tiles
     long long max_tiles = (long long)(ceil_div(n, tile_rows) + n_groups) * (ceil_div(n, kTileCols) + 1);
-    int grid = (int)min((long long)sms * 8, max(max_tiles, 1LL));
+    int grid = (int)min((long long)sms * 6, max(max_tiles, 1LL));
     nms_mask_kernel<O><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr,
-                                                  cmp == AIDET_CMP_GE ? 1 : 0, one, tile_rows, mask32, L.pitch32);
+                                                  cmp == AIDET_CMP_GE ? 1 : 0, one, tile_rows, mask32, L.pitch32,
+                                                  counters, local_prefix);
   }
   const int removed_cap = ceil_div(ceil_div(n, 32), 4) * 4;          // any group may hold all n boxes
   const int scan_pw = min(kScanPWMax, max(32, ceil_div(ceil_div(n, 32), 32) * 32));
-  size_t scan_smem = ((size_t)removed_cap + 2 * 32 * scan_pw) * 4;
+  const int sm_words = removed_cap + 2 * 32 * scan_pw;
+  size_t scan_smem = (size_t)sm_words * 4;
   if (scan_smem > 48 * 1024) {
     if (scan_smem > 227 * 1024) { set_error("nms: %d boxes exceed the single-group scan capacity", n); return AIDET_EINVAL; }
     AIDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
   }
-  nms_scan_kernel<<<n_groups, 256, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags, removed_cap, scan_pw);
-  nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
-  count_launch(6);        // + the CUB sort passes, which are library kernels and not counted
+  const bool fused_compact = n <= kFusedCompactMax;
+  nms_scan_kernel<<<n_groups, 256, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags, removed_cap, scan_pw,
+                                                   n, keep_out, n_keep, fused_compact ? counters + 1 : nullptr);
+  if (!fused_compact) nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
+  count_launch((small ? (local_prefix ? 3 : 4) : 5) + (fused_compact ? 0 : 1));        // + the CUB sort passes, which are library kernels and not counted
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;
 }
