@@ -38,6 +38,7 @@ if ROOT not in sys.path:
 F_PAIR = 256.0                       # FP32 flop charged per box pair
 FP32_PEAK_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12      # 74.4 TFLOP/s at the 1965 MHz maximum clock
 SCALES = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+TRAFFIC = {}
 
 
 def parse():
@@ -51,6 +52,16 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return p.parse_args()
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernels from the committed ncu capture (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
 
 
 def measured_peaks():
@@ -261,6 +272,8 @@ def run_ours(args, D):
     dev = torch.device("cuda", D.local)
     torch.cuda.set_device(dev)
     hbm_peak, hbm_src = measured_peaks()
+    global TRAFFIC
+    TRAFFIC = measured_traffic()
     G, r = D.world, D.rank
     line = {}
     sampler = ClockSampler(D.local) if r == 0 else None
@@ -352,7 +365,10 @@ def run_ours(args, D):
             "multi_gpu": multi,
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32-alu", "achieved": achieved, "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s",
-                         "frac": achieved / FP32_PEAK_NOMINAL, "traffic": None,
+                         "frac": achieved / FP32_PEAK_NOMINAL,
+                         "traffic": (TRAFFIC["riou_matrix_kernel"]["bytes_per_pair"] * kernel_pairs
+                                     if "riou_matrix_kernel" in TRAFFIC else None),
+                         "traffic_source": "ncu dram bytes per pair (%s) x pairs per launch" % TRAFFIC.get("source"),
                          "kernel": "riou_matrix_kernel<RectKind>", "kernel_ms": k_ms_avg,
                          "flop_per_pair": F_PAIR, "pairs_per_launch": kernel_pairs,
                          "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz (nominal max clock); FFMA micro-benchmark "
@@ -538,7 +554,10 @@ def run_ours(args, D):
                "roofline": {"bound": "hbm", "achieved": (bytes_fwd + bytes_bwd) / ((fms + bms) * 1e-3) / 1e9,
                             "peak": hbm_peak, "unit": "GB/s",
                             "frac": (bytes_fwd + bytes_bwd) / ((fms + bms) * 1e-3) / 1e9 / hbm_peak,
-                            "peak_source": hbm_src, "traffic": None,
+                            "peak_source": hbm_src,
+                            "traffic": ((TRAFFIC["rroi_align_fast_kernel_fwd"]["bytes"] + TRAFFIC["rroi_gather_kernel_bwd"]["bytes"])
+                                        if "rroi_gather_kernel_bwd" in TRAFFIC else None),
+                            "traffic_source": "ncu dram read+write of the fwd kernel + the gather-backward kernel, one C3 launch each (%s)" % TRAFFIC.get("source"),
                             "fwd_frac": bytes_fwd / (fms * 1e-3) / 1e9 / hbm_peak,
                             "bwd_frac": bytes_bwd / (bms * 1e-3) / 1e9 / hbm_peak}}
         if not args.no_e2e:
