@@ -118,3 +118,40 @@ def thetaobb_nms_by_bbox_nms(multi_bboxes, multi_scores, bbox_cls_inds, bbox_kee
 
 __all__ = ['multiclass_nms', 'multiclass_thetaobb_nms', 'multiclass_nms_with_index', 'thetaobb_nms_by_bbox_nms',
            'nms_wrapper']
+
+
+def get_det_rbboxes(rois, cls_score, rbbox_pred, img_shape, scale_factor, rescale=False, cfg=None,
+                    target_means=(0., 0., 0., 0., 0.), target_stds=(0.1, 0.1, 0.2, 0.2, 0.1), encode='thetaobb'):
+    """`RBBoxHead.get_det_rbboxes_parallel` (mmdet/models/bbox_heads/rbbox_head.py:253-296) with the rotated NMS
+    the reference left commented out (:294-295) in place of the HBB keep-index reuse (:288-293):
+    softmax -> decode (delta2thetaobb | delta2pointobb, core/rbbox/transforms.py:356-395,458-505) -> rescale ->
+    ONE batched rotated-NMS launch over all classes -> top `max_per_img`.  Everything stays on the device.
+
+    rois (n,5) [batch, x1, y1, x2, y2]; cls_score (n, C+1) logits (or a list to average, :271-272); rbbox_pred
+    (n, C*d) or None; cfg: object/dict with score_thr, polygon_nms_iou_thr (default 0.5, the dead config key of
+    configs/dota/dota_v002_theta_obb_r50_v1_train.py:130) and max_per_img, or None to get (rbboxes, scores) back.
+    """
+    import torch.nn.functional as TF
+    from ..rbbox import delta2pointobb, delta2thetaobb, pointobb_rescale, thetaobb_rescale
+    decode = {'thetaobb': delta2thetaobb, 'pointobb': delta2pointobb}
+    rescale_fn = {'thetaobb': thetaobb_rescale, 'pointobb': pointobb_rescale}
+    if encode not in decode:
+        raise NotImplementedError("encode %r: the kernels take theta-OBBs (5) or point-OBBs (8); convert H-OBBs with "
+                                  "hobb2pointobb first" % (encode,))
+    dim = 5 if encode == 'thetaobb' else 8
+    if isinstance(cls_score, list):
+        cls_score = sum(cls_score) / float(len(cls_score))
+    scores = TF.softmax(cls_score, dim=1) if cls_score is not None else None
+    if rbbox_pred is not None:
+        means = tuple(target_means) if len(target_means) == dim else (0.,) * dim
+        stds = tuple(target_stds) if len(target_stds) == dim else (1.,) * dim
+        rbboxes = decode[encode](rois[:, 1:], rbbox_pred, means, stds, img_shape)
+    else:
+        rbboxes = rois[:, 1:]
+    if rescale:
+        rbboxes = rescale_fn[encode](rbboxes.clone(), scale_factor, reverse_flag=True)
+    if cfg is None:
+        return rbboxes, scores
+    get = cfg.get if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+    return multiclass_thetaobb_nms(rbboxes, scores, get('score_thr', 0.05), get('polygon_nms_iou_thr', 0.5),
+                                   get('max_per_img', -1), out_dim_reg=dim)
