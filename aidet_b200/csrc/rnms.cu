@@ -78,16 +78,16 @@ struct NmsHbb {
 // "IoU cmp thr" without the division: inter cmp thr * (area_a + area_b - inter).  The union is either 0
 // (both boxes degenerate: IoU is defined 0 here, NaN > thr == false in the reference's HBB kernel) or far
 // above the denormal range.  `zero_hit` = what the comparison gives for IoU == 0.
-template <class O>
+template <class O, bool GE>
 __device__ __forceinline__ bool nms_hit(const typename O::Row& a, const typename O::Col& b, float area_b, float one,
-                                        float th, bool cmp_ge, bool zero_hit) {
+                                        float th, bool zero_hit) {
   if (O::disjoint(a, b)) return zero_hit;
   const float area_a = O::area(a, one);
   float inter = O::inter(a, b, one);
   if constexpr (O::FMT != 4) inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_b));
   const float den = area_a + area_b - inter;
   const float rhs = th * den;
-  const bool h = cmp_ge ? (inter >= rhs) : (inter > rhs);
+  const bool h = GE ? (inter >= rhs) : (inter > rhs);
   return den > 0.0f ? h : zero_hit;
 }
 
@@ -258,11 +258,11 @@ struct NmsTile { int start, ng, r0, cq0, nr, g; };   // nr == 0: no tile left
 // Tiles are handed out by a ticket counter (balanced although diagonal tiles are cheaper and groups differ in
 // size).  Thread 0 is the scheduler: while the CTA works on tile k it draws the ticket of tile k+1, skips tiles
 // left of the diagonal, and starts the TMA copy of its row records into the other staging buffer.
-template <class O>
+template <class O, bool GE>
 __global__ void __launch_bounds__(kTileCols)
 nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
                 const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
-                int n_groups, const float* __restrict__ thr, int n_thr, int cmp_ge, float one, int tile_rows,
+                int n_groups, const float* __restrict__ thr, int n_thr, float one, int tile_rows,
                 uint32_t* __restrict__ mask32, long long pitch32, int* __restrict__ ticket, int local_prefix) {
   using Row = typename O::Row; using Col = typename O::Col;
   __shared__ __align__(128) Row stage[2][kTileRows];
@@ -308,14 +308,13 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
   if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); schedule(0); }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool ge = cmp_ge != 0;
   for (int it = 0;; ++it) {
     const int buf = it & 1;
     const NmsTile d = desc[buf];
     if (d.nr == 0) break;
     if (threadIdx.x == 0) schedule(buf ^ 1);           // stage[buf^1] / desc[buf^1] were released by the last barrier
     const float th = thr[n_thr == 1 ? 0 : d.g];
-    const bool zero_hit = ge ? (0.0f >= th) : (0.0f > th);
+    const bool zero_hit = GE ? (0.0f >= th) : (0.0f > th);
     const int c0 = d.cq0 + warp * 32;
     const bool need = (c0 + 31 > d.r0) && (c0 < d.ng); // some column of the strip follows some row of the tile (warp-uniform)
     const int j = c0 + lane;
@@ -326,20 +325,29 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
     mbar_wait(&bar[buf], (it >> 1) & 1);
     if (need) {
       const Row* st = &stage[buf][0];
-      uint32_t word = 0;
-      for (int rr = 0; rr < d.nr; ++rr) {
-        const int i = d.r0 + rr;
-        uint32_t b = 0;
-        if (i < c0 + 31) {                             // otherwise no column of this strip follows row i
-          const bool hit = nms_hit<O>(st[rr], me, area_me, one, th, ge, zero_hit);
-          b = __ballot_sync(0xffffffffu, hit && live && j > i);
+      const bool above = d.r0 + d.nr - 1 < c0;         // every row of the tile precedes every column of the strip
+      for (int rb = 0; rb < d.nr; rb += 32) {          // 32 rows -> one half-word per lane
+        const int lim = min(32, d.nr - rb);
+        uint32_t word = 0;
+        if (above) {                                   // the common case: no per-row diagonal tests
+#pragma unroll 2
+          for (int k = 0; k < lim; ++k) {
+            const bool hit = nms_hit<O, GE>(st[rb + k], me, area_me, one, th, zero_hit);
+            const uint32_t b = __ballot_sync(0xffffffffu, hit && live);
+            if (lane == k) word = b;
+          }
+        } else {
+          for (int k = 0; k < lim; ++k) {
+            const int i = d.r0 + rb + k;
+            uint32_t b = 0;
+            if (i < c0 + 31) {                         // otherwise no column of this strip follows row i
+              const bool hit = nms_hit<O, GE>(st[rb + k], me, area_me, one, th, zero_hit);
+              b = __ballot_sync(0xffffffffu, hit && live && j > i);
+            }
+            if (lane == k) word = b;
+          }
         }
-        if (lane == (rr & 31)) word = b;
-        if ((rr & 31) == 31 || rr == d.nr - 1) {
-          const int row = d.r0 + (rr & ~31) + lane;
-          if (lane <= (rr & 31)) mask32[(long long)(d.start + row) * pitch32 + (c0 >> 5)] = word;
-          word = 0;
-        }
+        if (lane < lim) mask32[(long long)(d.start + d.r0 + rb + lane) * pitch32 + (c0 >> 5)] = word;
       }
     }
     __syncthreads();                                   // stage[buf] and desc[buf] are free again
@@ -597,9 +605,12 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     // upper bound of the tile count: every group padded to full tiles
     long long max_tiles = (long long)(ceil_div(n, tile_rows) + n_groups) * (ceil_div(n, kTileCols) + 1);
     int grid = (int)min((long long)sms * 6, max(max_tiles, 1LL));
-    nms_mask_kernel<O><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr,
-                                                  cmp == AIDET_CMP_GE ? 1 : 0, one, tile_rows, mask32, L.pitch32,
-                                                  counters, local_prefix);
+    if (cmp == AIDET_CMP_GE)
+      nms_mask_kernel<O, true><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr, one,
+                                                          tile_rows, mask32, L.pitch32, counters, local_prefix);
+    else
+      nms_mask_kernel<O, false><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr, one,
+                                                           tile_rows, mask32, L.pitch32, counters, local_prefix);
   }
   const int removed_cap = ceil_div(ceil_div(n, 32), 4) * 4;          // any group may hold all n boxes
   const int scan_pw = min(kScanPWMax, max(32, ceil_div(ceil_div(n, 32), 32) * 32));
