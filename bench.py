@@ -248,19 +248,37 @@ def group_pairs(groups, n_groups):
     return float((cnt * (cnt - 1) / 2).sum().item())
 
 
-def roi_touched_bytes(rois, lvl, batch, C, tile=1024):
-    """Exact |U_l| (distinct feature pixels touched by any bilinear tap) from the oracle, level by level."""
-    import numpy as np
-    from oracle import oracle as O
+def roi_touched_bytes(rois, lvl, batch, C, tile=1024, out=7, grid=2, device=None):
+    """|U_l| summed over the levels: distinct feature pixels touched by any bilinear tap of any RoI (BASELINE.md
+    section 3), counted with torch ops on `device` -- the sampling rule of roi_align_kernel_v2.cu:79-126 (aligned
+    variant, rotated about the RoI centre) restated here so that the product arm never touches oracle/."""
+    import torch
     total = 0
+    rois = rois.to(device).double()
+    lvl = lvl.to(device)
     for l, s in enumerate(SCALES):
-        sel = (lvl == l).nonzero().flatten()
-        if sel.numel() == 0:
+        r = rois[lvl == l]
+        if r.numel() == 0:
             continue
         hw = int(tile * s)
-        dummy = np.zeros((batch, hw, hw, 1), np.float32)
-        _, touched = O.roi_align_fwd(dummy, rois[sel].numpy(), s, (7, 7), 2, O.ROI_V2_ALIGNED, want_touched=True)
-        total += int(touched.sum())
+        b = r[:, 0].long()
+        cx, cy, w, h, th = r[:, 1] * s - 0.5, r[:, 2] * s - 0.5, r[:, 3] * s, r[:, 4] * s, r[:, 5]
+        k = (torch.arange(out * grid, device=device, dtype=torch.float64) + 0.5) / (out * grid) - 0.5      # sample offsets / side
+        yy = (h[:, None] * k[None, :])[:, :, None]
+        xx = (w[:, None] * k[None, :])[:, None, :]
+        cs, sn = torch.cos(th)[:, None, None], torch.sin(th)[:, None, None]
+        x = cx[:, None, None] + xx * cs - yy * sn
+        y = cy[:, None, None] + xx * sn + yy * cs
+        ok = ~((y < -1.0) | (y > hw) | (x < -1.0) | (x > hw))
+        x, y = x.clamp(min=0), y.clamp(min=0)
+        xl, yl = x.floor().long().clamp(max=hw - 1), y.floor().long().clamp(max=hw - 1)
+        xh, yh = (xl + 1).clamp(max=hw - 1), (yl + 1).clamp(max=hw - 1)
+        touched = torch.zeros((batch * hw * hw,), dtype=torch.bool, device=device)
+        base = (b * hw * hw)[:, None, None]
+        for yy_, xx_ in ((yl, xl), (yl, xh), (yh, xl), (yh, xh)):
+            idx = (base + yy_ * hw + xx_)[ok]
+            touched[idx] = True
+        total += int(touched.sum().item())
     return total
 
 
@@ -510,7 +528,7 @@ def run_ours(args, D):
         out = Fn.rroi_align_forward(feats, rois, SCALES, (7, 7), 2, 2, lvl)
         go = torch.randn(out.shape, generator=torch.Generator().manual_seed(9)).to(dev)
         grads = [torch.empty_like(f) for f in feats]
-        touched = roi_touched_bytes(rois_h, lvl_h, feats_h[0].shape[0], C)
+        touched = roi_touched_bytes(rois_h, lvl_h, feats_h[0].shape[0], C, device=dev)
         feat_elems = sum(f.numel() for f in feats)
         bytes_fwd = 4.0 * (C * touched + K * 49 * C + 6 * K)
         bytes_bwd = 4.0 * (K * 49 * C + C * touched + 6 * K) + 4.0 * feat_elems
@@ -657,7 +675,7 @@ def cpu_roi(sample_rois=512):
     rois, lvl = rois[:sample_rois], lvl[:sample_rois]
     C = feats[0].shape[3]
     go = np.random.RandomState(0).randn(sample_rois, 7, 7, C).astype(np.float32)
-    touched = roi_touched_bytes(rois, lvl, feats[0].shape[0], C)
+    touched = roi_touched_bytes(rois, lvl, feats[0].shape[0], C, device="cpu")
     t0 = time.perf_counter()
     for l, s in enumerate(SCALES):
         sel = (lvl == l).nonzero().flatten()
@@ -700,6 +718,9 @@ def run_reference(args):
     if rank != 0:
         return None
     cores = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is rank 0 alone and may use every host thread
+    # (the OpenMP runtime reads the variable when the oracle library is first loaded, which is below)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     n = args.iou_n
     sample = 4096
     for _ in range(args.warmup):
@@ -755,6 +776,7 @@ def main():
     D = Dist(args)
     line, dev = run_ours(args, D)
     if D.rank == 0 and not args.no_cpu and D.world == 1:
+        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
         cb = cpu_baselines(args)
         if "iou" in cb:
             line["cpu_baseline"] = cb.pop("iou")
