@@ -28,6 +28,8 @@ _SIGNATURES = {
     "aidet_riou_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "aidet_riou_matrix_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_longlong, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "aidet_riou_matrix_mcast_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_longlong, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "aidet_riou_matrix_multi_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_int, C.c_longlong, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "aidet_riou_aligned_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,

@@ -1,3 +1,3 @@
-from .geometry import rbbox_overlaps
+from .geometry import bbox_overlaps, rbbox_overlaps
 
-__all__ = ['rbbox_overlaps']
+__all__ = ['bbox_overlaps', 'rbbox_overlaps']

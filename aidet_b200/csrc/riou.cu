@@ -41,6 +41,18 @@ struct QuadKind {
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.my; }
 };
 
+// fmt 4: axis-aligned (x1,y1,x2,y2) boxes with the legacy +1 pixel convention of mmdet/core/bbox/geometry.py:57-86
+// (bbox_overlaps) -- the same tiled kernel; this one is bound by the 4 B/pair result store, not by arithmetic.
+struct HbbKind {
+  using Row = HbbBox; using Col = HbbBox;
+  static constexpr int FMT = 4;
+  __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) {
+    HbbBox b{p[0], p[1], p[2], p[3]};
+    if (r) *r = b;
+    if (c) *c = b;
+  }
+};
+
 // Matrix-row boxes are staged as Row records (the box that is transformed), matrix-column
 // boxes live in registers as Col records (the box whose frame is used).
 template <class K>
@@ -52,6 +64,12 @@ struct PairOp {
     if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;
     return finish_overlap(K::inter(s, r), s.area, r.area, mode);
   }
+};
+
+template <>
+struct PairOp<HbbKind> {
+  using S = HbbBox; using R = HbbBox;
+  __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) { return hbb_overlap(s, r, 1.0f, mode); }
 };
 
 template <class K>
@@ -79,7 +97,15 @@ constexpr int kMaxTileRows = 64;
 constexpr int kMaxPeers = 8;
 struct OutSet { float* p[kMaxPeers]; int n; };
 
-template <class K, int MODE, bool MULTI>
+// NVSwitch multicast store: ONE store instruction, the switch replicates it into every GPU of the multicast group
+// (NVLS), so a row-sharded rank sends its block over its NVLink once instead of once per peer.
+__device__ __forceinline__ void st_multicast(float* mc_ptr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_ptr), "f"(v) : "memory");
+}
+
+enum { STORE_LOCAL = 0, STORE_PEERS = 1, STORE_MCAST = 2 };
+
+template <class K, int MODE, int STORE>
 __global__ void __launch_bounds__(kColsPerTile)
 riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
                    const typename PairOp<K>::R* __restrict__ cols, int n,
@@ -129,9 +155,11 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     for (int r = 0; r < nr; ++r) {
       float v = P::overlap(st[r], me, MODE);
       if (live) {
-        if (MULTI) {
+        if (STORE == STORE_PEERS) {
 #pragma unroll
           for (int q = 0; q < kMaxPeers; ++q) if (q < outs.n) __stcs(outs.p[q] + off, v);
+        } else if (STORE == STORE_MCAST) {
+          st_multicast(outs.p[0] + off, v);
         } else {
           __stcs(outs.p[0] + off, v);
         }
@@ -158,7 +186,7 @@ __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restri
 
 template <class K>
 static int launch_matrix(const float* a, int m, const float* b, int n, int mode, const OutSet& outs, long long ld,
-                         void* ws, int device, cudaStream_t s) {
+                         void* ws, int device, cudaStream_t s, bool mcast = false) {
   using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
   S* rows = reinterpret_cast<S*>(ws);
@@ -180,11 +208,12 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   grid = ceil_div(n_tiles, tiles_per_cta);
   {
     ProfScope prof(PROF_RIOU, s);
-#define AIDET_LAUNCH_RIOU(MODE_, MULTI_)                                                                        \
-  riou_matrix_kernel<K, MODE_, MULTI_><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, outs, ld, tile_rows,     \
+#define AIDET_LAUNCH_RIOU(MODE_, STORE_)                                                                        \
+  riou_matrix_kernel<K, MODE_, STORE_><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, outs, ld, tile_rows,     \
                                                                       n_row_tiles, n_tiles, tiles_per_cta)
-    if (outs.n > 1) { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, true); else AIDET_LAUNCH_RIOU(MODE_IOU, true); }
-    else            { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, false); else AIDET_LAUNCH_RIOU(MODE_IOU, false); }
+    if (mcast)           { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_MCAST); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_MCAST); }
+    else if (outs.n > 1) { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_PEERS); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_PEERS); }
+    else                 { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_LOCAL); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_LOCAL); }
 #undef AIDET_LAUNCH_RIOU
   }
   count_launch(3);
@@ -199,13 +228,13 @@ using namespace aidet;
 extern "C" {
 
 size_t aidet_riou_workspace_bytes(int m, int n, int fmt) {
-  size_t rec = (fmt == 8) ? 64 : 32;
+  size_t rec = (fmt == 8) ? 64 : (fmt == 4 ? 16 : 32);
   return align_up((size_t)(m > 0 ? m : 0) * rec, 128) + align_up((size_t)(n > 0 ? n : 0) * rec, 128) + 128;
 }
 
 int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt, int mode, float* out,
                           long long ld_out, void* workspace, size_t ws_bytes, int device, void* stream) {
-  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_matrix_f32: fmt must be 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(fmt == 4 || fmt == 5 || fmt == 8, "aidet_riou_matrix_f32: fmt must be 4, 5 or 8, got %d", fmt);
   AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_matrix_f32: bad mode %d", mode);
   AIDET_REQUIRE(m >= 0 && n >= 0, "aidet_riou_matrix_f32: negative size");
   if (m == 0 || n == 0) return AIDET_OK;
@@ -220,6 +249,7 @@ int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt,
   cudaStream_t s = (cudaStream_t)stream;
   OutSet outs{}; outs.p[0] = out; outs.n = 1;
   if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
+  if (fmt == 4) return launch_matrix<HbbKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
   return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
 }
 
@@ -250,9 +280,29 @@ int aidet_riou_matrix_multi_f32(const float* a, int m, const float* b, int n, in
   return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
 }
 
+int aidet_riou_matrix_mcast_f32(const float* a, int m, const float* b, int n, int fmt, int mode, float* out_mc,
+                                long long ld_out, void* workspace, size_t ws_bytes, int device, void* stream) {
+  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_matrix_mcast_f32: fmt must be 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_matrix_mcast_f32: bad mode %d", mode);
+  AIDET_REQUIRE(m >= 0 && n >= 0, "aidet_riou_matrix_mcast_f32: negative size");
+  if (m == 0 || n == 0) return AIDET_OK;
+  AIDET_REQUIRE(a && b && out_mc && workspace, "aidet_riou_matrix_mcast_f32: null pointer");
+  AIDET_REQUIRE(ld_out >= n, "aidet_riou_matrix_mcast_f32: ld_out %lld < n %d", ld_out, n);
+  AIDET_REQUIRE(((uintptr_t)workspace & 15) == 0, "aidet_riou_matrix_mcast_f32: workspace must be 16 B aligned");
+  if (ws_bytes < aidet_riou_workspace_bytes(m, n, fmt)) {
+    set_error("aidet_riou_matrix_mcast_f32: workspace %zu < %zu", ws_bytes, aidet_riou_workspace_bytes(m, n, fmt));
+    return AIDET_EWORKSPACE;
+  }
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  OutSet outs{}; outs.p[0] = out_mc; outs.n = 1;
+  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s, true);
+  return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s, true);
+}
+
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out, int device,
                            void* stream) {
-  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_aligned_f32: fmt must be 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(fmt == 4 || fmt == 5 || fmt == 8, "aidet_riou_aligned_f32: fmt must be 4, 5 or 8, got %d", fmt);
   AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_aligned_f32: bad mode %d", mode);
   AIDET_REQUIRE(n >= 0, "aidet_riou_aligned_f32: negative size");
   if (n == 0) return AIDET_OK;
@@ -260,6 +310,7 @@ int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int m
   if (int rc = set_device(device)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   if (fmt == 5) riou_aligned_kernel<RectKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
+  else if (fmt == 4) riou_aligned_kernel<HbbKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
   else riou_aligned_kernel<QuadKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
   count_launch(1);
   AIDET_CUDA(cudaGetLastError());

@@ -64,6 +64,26 @@ def riou_matrix_multi(a, b, dst_ptrs, ld, mode="iou"):
                 "aidet_riou_matrix_multi_f32")
 
 
+def riou_matrix_mcast(a, b, mc_ptr, ld, mode="iou"):
+    """Overlap matrix of a (m,fmt) x b (n,fmt) stored ONCE to the NVSwitch multicast address `mc_ptr` (row stride
+    `ld` elements); the switch replicates every store into all GPUs of the multicast group (see aidet_b200.sharded)."""
+    assert mode in ("iou", "iof")
+    fmt = a.size(-1)
+    a, b = _f32c(a, fmt, "a"), _f32c(b, fmt, "b")
+    m, n = a.size(0), b.size(0)
+    if m == 0 or n == 0:
+        return
+    dev = a.device.index
+    lib = L.lib()
+    ws_bytes = lib.aidet_riou_workspace_bytes(m, n, fmt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(dev):
+        L.check(lib.aidet_riou_matrix_mcast_f32(L.dptr(a), m, L.dptr(b), n, fmt,
+                                                L.MODE_IOF if mode == "iof" else L.MODE_IOU, C.c_void_p(int(mc_ptr)),
+                                                int(ld), L.dptr(ws), ws_bytes, dev, L.stream_ptr(dev)),
+                "aidet_riou_matrix_mcast_f32")
+
+
 def riou_aligned(a, b, mode="iou"):
     assert mode in ("iou", "iof")
     fmt = a.size(-1)

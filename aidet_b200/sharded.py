@@ -91,22 +91,30 @@ class SymmetricMatrix:
         self.tensor = symm_mem.empty((self.rows_per * world, n), dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
         self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        # NVSwitch multicast mapping of the same allocation (0 when the fabric / driver has no NVLS)
+        self.mc_ptr = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
 
     def barrier(self):
         self.handle.barrier()
 
 
-def sharded_rbbox_overlaps_fused(rbboxes1, rbboxes2, sym, mode='iou'):
+def sharded_rbbox_overlaps_fused(rbboxes1, rbboxes2, sym, mode='iou', multicast=False):
     """Row-sharded overlap matrix with the all-gather fused into the kernel: rank r computes its row block and
     stores every tile to the same rows of ALL ranks' `sym` buffers (aidet_riou_matrix_multi_f32), so when the
     kernels and the closing barrier are done every rank holds the whole matrix.  No NCCL call on the data path.
+    multicast=True (needs `sym.mc_ptr`): every element is stored once to the NVSwitch multicast address and the
+    switch replicates it (aidet_riou_matrix_mcast_f32) -- the rank's link carries its block once, not world-1 times.
     """
     from .ops import functional as F
     m, n = rbboxes1.size(0), rbboxes2.size(0)
     assert (m, n) == (sym.m, sym.n)
     rows_per, r0, r1 = shard_rows(m, sym.world, sym.rank)
     sym.barrier()                    # nobody is still reading the previous result
-    if r1 > r0 and n > 0:
+    if r1 > r0 and n > 0 and multicast:
+        if not sym.mc_ptr:
+            raise RuntimeError("this symmetric-memory allocation has no multicast mapping (no NVLS on this box)")
+        F.riou_matrix_mcast(rbboxes1[r0:r1].contiguous(), rbboxes2, sym.mc_ptr + sym.rank * rows_per * n * 4, n, mode)
+    elif r1 > r0 and n > 0:
         off = sym.rank * rows_per * n * 4
         # own copy first, then the peers in ring order so the ranks do not all target the same GPU at once
         dst = [sym.ptrs[(sym.rank + q) % sym.world] + off for q in range(sym.world)]

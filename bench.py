@@ -365,6 +365,34 @@ def run_ours(args, D):
                            "buffer from inside the kernel (NVLink peer stores), two symmetric-memory barriers, no NCCL on the data path"}
                 if same and fms_step < ms_step:
                     ms_step, launches, k_ms_avg = fms_step, flaunches, D.max_float(fk_ms / max(fk_cnt, 1), dev)
+                # NVSwitch multicast form: one multimem.st per element, replicated by the switch (NVLS)
+                has_mc = D.max_float(0.0 if sym.mc_ptr else 1.0, dev) == 0.0
+                if has_mc and os.environ.get("AIDET_BENCH_NO_MCAST") != "1":
+                    def step_mcast():
+                        sharded.sharded_rbbox_overlaps_fused(a_dev[:n], b_dev, sym, multicast=True)
+
+                    sym.tensor.zero_()
+                    L.prof_read(L.PROF_RIOU, reset=True)
+                    mms, mlaunches = timed(D, dev, args.steps, args.warmup, step_mcast)
+                    mk_ms, mk_cnt = L.prof_read(L.PROF_RIOU, reset=True)
+                    mms_step = mms / args.steps
+                    sym.tensor.zero_()
+                    step_mcast()
+                    torch.cuda.synchronize(dev)
+                    same_mc = bool(torch.equal(sym.tensor[:n][probe], out[:n][probe]))
+                    same_mc = D.max_float(0.0 if same_mc else 1.0, dev) == 0.0
+                    own = float(rows_per) * n * 4
+                    multi["fused_multicast_stores"] = {
+                        "value": pairs / mms_step / 1e6, "unit": "Gpairs/s", "ms_per_step": mms_step,
+                        "kernel_ms": D.max_float(mk_ms / max(mk_cnt, 1), dev), "matches_nccl_path": same_mc,
+                        "nvlink_bytes_out_per_rank": own, "nvlink_bytes_in_per_rank": own * (G - 1),
+                        "nvlink_in_gbs": own * (G - 1) / (mms_step * 1e-3) / 1e9,
+                        "how": "aidet_riou_matrix_mcast_f32: every element stored once with multimem.st to the symmetric "
+                               "buffer's multicast address; the NVSwitch replicates it into all ranks (this one included)"}
+                    if same_mc and mms_step < ms_step:
+                        ms_step, launches, k_ms_avg = mms_step, mlaunches, D.max_float(mk_ms / max(mk_cnt, 1), dev)
+                else:
+                    multi["fused_multicast_stores"] = {"unavailable": "no multicast mapping for the symmetric allocation"}
                 del sym
             except Exception as exc:       # symmetric memory unavailable on this box: the NCCL number stands
                 multi["fused_peer_stores"] = {"unavailable": repr(exc)[:300]}

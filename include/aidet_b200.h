@@ -58,7 +58,9 @@ int aidet_ffma_peak(int device, int iters, double* tflops_out, void* stream);
  * Replaces: the polygon IoU AIDet reaches through wwtool (mmdet/datasets/dota.py:23,336)
  * and the (m,n) overlap API of mmdet/core/bbox/geometry.py:4-88 for rotated boxes.
  * a: (m,fmt) row-major, b: (n,fmt); out: m rows of n floats, row stride ld_out
- * (elements).  workspace >= aidet_riou_workspace_bytes(m,n,fmt), 16 B aligned. */
+ * (elements).  workspace >= aidet_riou_workspace_bytes(m,n,fmt), 16 B aligned.
+ * fmt 4 = axis-aligned boxes with the legacy +1 convention: bbox_overlaps itself
+ * (mmdet/core/bbox/geometry.py:57-86), served by the same tiled kernel. */
 size_t aidet_riou_workspace_bytes(int m, int n, int fmt);
 int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt, int mode,
                           float* out, long long ld_out, void* workspace, size_t ws_bytes,
@@ -71,6 +73,12 @@ int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt,
 int aidet_riou_matrix_multi_f32(const float* a, int m, const float* b, int n, int fmt, int mode,
                                 float* const* outs_host, int n_outs, long long ld_out,
                                 void* workspace, size_t ws_bytes, int device, void* stream);
+/* Same exchange through NVSwitch multicast (NVLS): out_mc is the MULTICAST address of the row block (e.g. torch
+ * symmetric memory's multicast_ptr + offset); every element is stored once with multimem.st and the switch
+ * replicates it into all GPUs of the multicast group, this one included -- the rank's NVLink carries its block
+ * once instead of once per peer.  Needs a multicast-capable allocation; the caller synchronises the ranks. */
+int aidet_riou_matrix_mcast_f32(const float* a, int m, const float* b, int n, int fmt, int mode, float* out_mc,
+                                long long ld_out, void* workspace, size_t ws_bytes, int device, void* stream);
 /* element-wise pairs (is_aligned=True, geometry.py:57-71): out[i] = ovr(a[i], b[i]) */
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out,
                            int device, void* stream);

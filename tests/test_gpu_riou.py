@@ -128,3 +128,31 @@ def test_cpu_tensor_raises():
     a, _ = synth.dota_boxes(4, seed=1)
     with pytest.raises(NotImplementedError):
         rbbox_overlaps(a, a)
+
+
+@pytest.mark.gpu
+def test_hbb_bbox_overlaps_reference_doctest_and_oracle(cuda):
+    """bbox_overlaps (mmdet/core/bbox/geometry.py:4-88) served by the tiled kernel, fmt 4: the doctest matrix of
+    geometry.py:22-44, the empty-shape contracts of :54-55, random boxes against the oracle restatement, iof, aligned."""
+    from aidet_b200.core import bbox_overlaps
+    b1 = torch.tensor([[0, 0, 10, 10], [10, 10, 20, 20], [32, 32, 38, 42]], dtype=torch.float32, device=cuda)
+    b2 = torch.tensor([[0, 0, 10, 20], [0, 10, 10, 19], [10, 10, 20, 20]], dtype=torch.float32, device=cuda)
+    got = bbox_overlaps(b1, b2)
+    want = torch.tensor([[0.5238, 0.0500, 0.0041], [0.0323, 0.0452, 1.0000], [0.0000, 0.0000, 0.0000]])
+    assert torch.allclose(got.cpu(), want, atol=1e-4)
+    empty = torch.empty(0, 4, device=cuda)
+    nonempty = torch.tensor([[0., 0., 10., 9.]], device=cuda)
+    assert tuple(bbox_overlaps(empty, nonempty).shape) == (0, 1)
+    assert tuple(bbox_overlaps(nonempty, empty).shape) == (1, 0)
+    assert tuple(bbox_overlaps(empty, empty).shape) == (0, 0)
+    g = torch.Generator().manual_seed(3)
+    xy = torch.rand(700, 2, generator=g) * 300
+    a = torch.cat([xy, xy + torch.rand(700, 2, generator=g) * 80], 1)
+    xy = torch.rand(533, 2, generator=g) * 300
+    b = torch.cat([xy, xy + torch.rand(533, 2, generator=g) * 80], 1)
+    for mode in ("iou", "iof"):
+        ref = O.hbb_overlaps(a.numpy(), b.numpy(), mode=mode, plus_one=True)
+        got = bbox_overlaps(a.to(cuda), b.to(cuda), mode=mode).cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-5
+        al = bbox_overlaps(a[:533].to(cuda), b.to(cuda), mode=mode, is_aligned=True).cpu().numpy()
+        assert np.abs(al - np.diag(O.hbb_overlaps(a[:533].numpy(), b.numpy(), mode=mode, plus_one=True))).max() <= 1e-5
