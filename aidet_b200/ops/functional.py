@@ -169,6 +169,44 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
     return keep[:k]
 
 
+def soft_nms_batched(dets, group_ids=None, iou_thr=0.3, method=1, sigma=0.5, min_score=1e-3, n_groups=None):
+    """Soft-NMS of dets (n,5) [x1,y1,x2,y2,score] per group (one CTA per group, all groups in one launch).
+
+    Returns (rows (k,6) [x1,y1,x2,y2,decayed score,original index], counts (n_groups,) int64): the rows of
+    group g are the `counts[g]` rows after those of the groups before it, in the reference's selection order
+    (nms_cpu.cpp:190-199)."""
+    dets = _f32c(dets, 5, "dets")
+    n = dets.size(0)
+    device = dets.device
+    if group_ids is None:
+        n_groups = 1
+        order = torch.arange(n, device=device)
+        offsets = torch.tensor([0, n], dtype=torch.int32, device=device)
+        max_group = n
+    else:
+        gids = group_ids.reshape(-1).to(device=device, dtype=torch.long)
+        if n_groups is None:
+            n_groups = int(gids.max().item()) + 1 if n else 1
+        order = torch.argsort(gids, stable=True)                     # groups contiguous, original order inside
+        cnt = torch.bincount(gids, minlength=n_groups)
+        offsets = torch.zeros(n_groups + 1, dtype=torch.int32, device=device)
+        offsets[1:] = torch.cumsum(cnt, 0).int()
+        max_group = int(cnt.max().item()) if n else 0
+    rows = torch.cat([dets[order], order.float()[:, None]], dim=1).contiguous()
+    n_out = torch.zeros(n_groups, dtype=torch.int32, device=device)
+    if n:
+        dev = device.index
+        with torch.cuda.device(dev):
+            L.check(L.lib().aidet_soft_nms_f32(L.dptr(rows), L.dptr(offsets), n_groups, max_group, float(iou_thr),
+                                               int(method), float(sigma), float(min_score), L.dptr(n_out), dev,
+                                               L.stream_ptr(dev)), "aidet_soft_nms_f32")
+    counts = n_out.long()
+    pos = torch.arange(n, device=device)
+    grp = torch.bucketize(pos, offsets[1:].long(), right=True).clamp(max=n_groups - 1)
+    keep = (pos - offsets.long()[grp]) < counts[grp]
+    return rows[keep], counts
+
+
 def _level_tables(tensors):
     n = len(tensors)
     ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])

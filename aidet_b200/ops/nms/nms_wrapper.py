@@ -90,6 +90,37 @@ def batched_rnms(rboxes, scores, group_ids, iou_thr, n_groups=None):
 
 
 def soft_nms(dets, iou_thr, method='linear', sigma=0.5, min_score=1e-3):
-    """mmdet/ops/nms/nms_wrapper.py:63-118 is a CPU-only op in the reference (nms_cpu.cpp:70-201)
-    and is outside the accelerated path."""
-    raise NotImplementedError('soft_nms is CPU-only in the reference and not part of the B200 hot path')
+    """Soft-NMS with the reference's contract (mmdet/ops/nms/nms_wrapper.py:63-118): tensor or ndarray in, same
+    container out, `(new_dets (k,5) with decayed scores, inds (k,))` in selection order.
+
+    The reference has only a CPU kernel (nms_cpu.cpp:70-201) and round-trips CUDA tensors through the host
+    (nms_wrapper.py:92-94,110-114); here the same loop runs on the device (aidet_soft_nms_f32).  CPU tensors and
+    ndarrays are uploaded -- there is no CPU implementation.
+
+    Example (nms_wrapper.py:81-90):
+        >>> dets = np.array([[4., 3., 5., 3., 0.9],
+        >>>                  [4., 3., 5., 4., 0.9],
+        >>>                  [3., 1., 3., 1., 0.5],
+        >>>                  [3., 1., 3., 1., 0.5],
+        >>>                  [3., 1., 3., 1., 0.4],
+        >>>                  [3., 1., 3., 1., 0.0]], dtype=np.float32)
+        >>> new_dets, inds = soft_nms(dets, 0.7, sigma=0.5)
+        >>> assert len(inds) == len(new_dets) == 3
+    """
+    is_numpy, dets_th, _ = _to_device(dets, None)
+    method_codes = {'linear': 1, 'gaussian': 2}
+    if method not in method_codes:
+        raise ValueError('Invalid method for SoftNMS: {}'.format(method))
+    if dets_th.dim() != 2 or dets_th.size(1) != 5:
+        raise ValueError('soft_nms expects dets of shape (N, 5), got {}'.format(tuple(dets_th.shape)))
+    if dets_th.shape[0] == 0:
+        new_dets, inds = dets_th.new_zeros((0, 5)), dets_th.new_zeros(0, dtype=torch.long)
+    else:
+        dev = _cuda_device(dets_th, None)
+        rows, _ = F.soft_nms_batched(dets_th.to(device=dev, dtype=torch.float32), None, float(iou_thr),
+                                     method_codes[method], float(sigma), float(min_score))
+        new_dets = rows[:, :5].to(device=dets_th.device, dtype=dets_th.dtype)
+        inds = rows[:, 5].to(device=dets_th.device, dtype=torch.long)
+    if is_numpy:
+        return new_dets.numpy().astype(dets.dtype), inds.numpy().astype(np.int64)
+    return new_dets, inds

@@ -100,6 +100,18 @@ int aidet_nms_batched_f32(const float* boxes, int fmt, const float* scores, cons
                           long long* keep_out, int* n_keep, void* workspace, size_t ws_bytes,
                           int device, void* stream);
 
+/* ---- Soft-NMS (axis-aligned, +1 convention), batched over groups ------------
+ * Replaces: soft_nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:70-201), the reference's only Soft-NMS -- CUDA
+ * tensors are copied to the host and back around it (mmdet/ops/nms/nms_wrapper.py:92-94,110-114).
+ *   rows (n_total, 6) float32 IN/OUT: on entry [x1, y1, x2, y2, score, original index]; the rows of group g are
+ *     rows[group_offsets[g] .. group_offsets[g+1]); on return the first n_out[g] rows of every group are its
+ *     detections in selection order with decayed scores -- the (k, 6) result of nms_cpu.cpp:190-199.
+ *   group_offsets (n_groups + 1) int32 device array; max_group = largest group size (host value)
+ *   method 1 = linear, 2 = gaussian (nms_wrapper.py:104), 0 = hard; iou_thr, sigma, min_score as the reference
+ * One CTA per group; same operation order in IEEE single precision as the C++ float instantiation. */
+int aidet_soft_nms_f32(float* rows, const int* group_offsets, int n_groups, int max_group, float iou_thr, int method,
+                       float sigma, float min_score, int* n_out, int device, void* stream);
+
 /* ---- rotated / axis-aligned RoIAlign, multi-level, NHWC -------------------
  * Replaces: roi_align_cuda.forward_v1/v2, backward_v1/v2
  * (mmdet/ops/roi_align/src/roi_align_kernel.cu:64-141,187-283, roi_align_kernel_v2.cu:62-348)
