@@ -132,13 +132,13 @@ def get_det_rbboxes(rois, cls_score, rbbox_pred, img_shape, scale_factor, rescal
     configs/dota/dota_v002_theta_obb_r50_v1_train.py:130) and max_per_img, or None to get (rbboxes, scores) back.
     """
     import torch.nn.functional as TF
-    from ..rbbox import delta2pointobb, delta2thetaobb, pointobb_rescale, thetaobb_rescale
-    decode = {'thetaobb': delta2thetaobb, 'pointobb': delta2pointobb}
-    rescale_fn = {'thetaobb': thetaobb_rescale, 'pointobb': pointobb_rescale}
+    from ..rbbox import (delta2hobb, delta2pointobb, delta2thetaobb, hobb2pointobb, hobb_rescale, pointobb_rescale,
+                         thetaobb_rescale)
+    decode = {'thetaobb': delta2thetaobb, 'pointobb': delta2pointobb, 'hobb': delta2hobb}
+    rescale_fn = {'thetaobb': thetaobb_rescale, 'pointobb': pointobb_rescale, 'hobb': hobb_rescale}
     if encode not in decode:
-        raise NotImplementedError("encode %r: the kernels take theta-OBBs (5) or point-OBBs (8); convert H-OBBs with "
-                                  "hobb2pointobb first" % (encode,))
-    dim = 5 if encode == 'thetaobb' else 8
+        raise ValueError("unknown encode %r (thetaobb | pointobb | hobb)" % (encode,))
+    dim = 8 if encode == 'pointobb' else 5
     if isinstance(cls_score, list):
         cls_score = sum(cls_score) / float(len(cls_score))
     scores = TF.softmax(cls_score, dim=1) if cls_score is not None else None
@@ -153,5 +153,9 @@ def get_det_rbboxes(rois, cls_score, rbbox_pred, img_shape, scale_factor, rescal
     if cfg is None:
         return rbboxes, scores
     get = cfg.get if isinstance(cfg, dict) else (lambda k, d=None: getattr(cfg, k, d))
+    if encode == 'hobb':        # the NMS kernels take theta-OBBs or corner lists: H-OBB -> 8 points (transforms.py:137-163)
+        n = rbboxes.size(0)
+        rbboxes = hobb2pointobb(rbboxes.reshape(n, -1, 5)).reshape(n, -1)
+        dim = 8
     return multiclass_thetaobb_nms(rbboxes, scores, get('score_thr', 0.05), get('polygon_nms_iou_thr', 0.5),
                                    get('max_per_img', -1), out_dim_reg=dim)

@@ -10,6 +10,8 @@ These define what (cx, cy, w, h, theta) and the 8-point order MEAN for the kerne
     delta2thetaobb     transforms.py:356-395
     pointobb2delta     transforms.py:412-456
     delta2pointobb     transforms.py:458-505
+    hobb2pointobb      transforms.py:137-163 H-OBB (first edge + height) -> corners
+    hobb2delta / delta2hobb / hobb_rescale  transforms.py:522-600,308-319
     rbbox2result       transforms.py:615-633
 The reference's list-in / list-out helpers take one box; the tensor forms here take (..., 5) / (..., 8).
 """
@@ -125,6 +127,60 @@ def delta2pointobb(rois, deltas, means=(0,) * 8, stds=(1,) * 8, max_shape=None, 
     x1, y1, x2, y2 = (rois[:, i].unsqueeze(1) for i in range(4))
     out = torch.stack([pw * d[:, 0::8] + x1, ph * d[:, 1::8] + y1, pw * d[:, 2::8] + x2, ph * d[:, 3::8] + y1,
                        pw * d[:, 4::8] + x2, ph * d[:, 5::8] + y2, pw * d[:, 6::8] + x1, ph * d[:, 7::8] + y2], dim=-1)
+    return out.view_as(deltas)
+
+
+def hobb2pointobb(hobb, truncate=None):
+    """(..., 5) H-OBB [x1, y1, x2, y2, h] (first edge p1->p2 plus the box height) -> (..., 8) corners
+    (transforms.py:137-163): p3 = p2 + h * (-cos a, sin a), p4 = p1 + h * (-cos a, sin a) with
+    a = pi/2 - atan2(y2 - y1, x2 - x1).  The reference's list form truncates every coordinate to int (:161);
+    that is kept for list / ndarray input (truncate=None -> True) and off for tensors (decoded predictions stay
+    float until the NMS), override with `truncate`."""
+    single = not isinstance(hobb, torch.Tensor)
+    t = torch.as_tensor(np.asarray(hobb, dtype=np.float64)) if single else hobb
+    x1, y1, x2, y2, h = t.unbind(-1)
+    ang = math.pi / 2.0 - torch.atan2(y2 - y1, x2 - x1)
+    dx, dy = h * torch.cos(ang), h * torch.sin(ang)
+    out = torch.stack([x1, y1, x2, y2, x2 - dx, y2 + dy, x1 - dx, y1 + dy], dim=-1)
+    if truncate if truncate is not None else single:
+        out = out.trunc()
+    return [int(v) for v in out.tolist()] if single and out.dim() == 1 else (out.tolist() if single else out)
+
+
+def hobb_rescale(hobbs, scale_factor, reverse_flag=False):
+    """transforms.py:308-319 (in place)."""
+    if not reverse_flag:
+        hobbs *= scale_factor
+    else:
+        hobbs /= scale_factor
+    return hobbs
+
+
+def hobb2delta(proposals, gt, means=(0, 0, 0, 0, 0), stds=(1, 1, 1, 1, 1)):
+    """proposals (n,4), gt (n,5) [x1,y1,x2,y2,h] -> (n,5) deltas (transforms.py:522-556)."""
+    assert proposals.size(0) == gt.size(0)
+    proposals, gt = proposals.float(), gt.float()
+    pw = proposals[..., 2] - proposals[..., 0] + 1.0
+    ph = proposals[..., 3] - proposals[..., 1] + 1.0
+    x1, y1, x2 = proposals[..., 0], proposals[..., 1], proposals[..., 2]
+    deltas = torch.stack([(gt[..., 0] - x1) / pw, (gt[..., 1] - y1) / ph, (gt[..., 2] - x2) / pw, (gt[..., 3] - y1) / ph,
+                          (gt[..., 4] + 1.0 - ph) / ph], dim=-1)
+    means = deltas.new_tensor(means).unsqueeze(0)
+    stds = deltas.new_tensor(stds).unsqueeze(0)
+    return deltas.sub_(means).div_(stds)
+
+
+def delta2hobb(rois, deltas, means=(0, 0, 0, 0, 0), stds=(1, 1, 1, 1, 1), max_shape=None, wh_ratio_clip=16 / 1000):
+    """rois (n,4), deltas (n,5k) -> (n,5k) H-OBBs (transforms.py:558-600)."""
+    k = deltas.size(1) // 5
+    d = deltas * deltas.new_tensor(stds).repeat(1, k) + deltas.new_tensor(means).repeat(1, k)
+    max_ratio = abs(math.log(wh_ratio_clip))
+    dh = d[:, 4::5].clamp(min=-max_ratio, max=max_ratio)
+    pw = (rois[:, 2] - rois[:, 0] + 1.0).unsqueeze(1)
+    ph = (rois[:, 3] - rois[:, 1] + 1.0).unsqueeze(1)
+    x1, y1, x2 = (rois[:, i].unsqueeze(1) for i in range(3))
+    out = torch.stack([pw * d[:, 0::5] + x1, ph * d[:, 1::5] + y1, pw * d[:, 2::5] + x2, ph * d[:, 3::5] + y1,
+                       ph * dh + ph], dim=-1)
     return out.view_as(deltas)
 
 

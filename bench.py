@@ -528,6 +528,30 @@ def run_ours(args, D):
         nms["workload"] = ("C2: 2000 proposals x 15 classes, score>0.05 candidates, thr 0.5, one launch over all "
                            "classes (c2 = DOTA-shaped, c2_dense = every pair intersects, c2x8 = 8 tiles batched); "
                            "L2 flushed between steps; time = sort+gather+mask+scan+compact+count readback")
+        if G == 1:
+            # Soft-NMS (nms_cpu.cpp:70-201 is the reference's only implementation): all 15 classes in one launch
+            sd, sg, sng = soft_nms_inputs()
+            sdd, sgd = sd.to(dev), sg.to(dev)
+            ms, launches = timed(D, dev, args.steps, args.warmup,
+                                 lambda: Fn.soft_nms_batched(sdd, sgd, 0.3, 1, 0.5, 0.05, n_groups=sng), flush=flush)
+            srows, scnt = Fn.soft_nms_batched(sdd, sgd, 0.3, 1, 0.5, 0.05, n_groups=sng)
+            shost = sd.pin_memory()
+            sghost = sg.pin_memory()
+
+            def soft_e2e():
+                rws, cnt = Fn.soft_nms_batched(shost.to(dev, non_blocking=True), sghost.to(dev, non_blocking=True), 0.3, 1,
+                                               0.5, 0.05, n_groups=sng)
+                return rws.cpu(), cnt.cpu()
+            sems = wall_timed(D, dev, args.steps, args.warmup, soft_e2e)
+            nms["soft_nms"] = {"value": sd.shape[0] / (ms / args.steps) / 1e3, "unit": "Mboxes/s", "ms_per_step": ms / args.steps,
+                               "boxes": int(sd.shape[0]), "groups": int(sng), "kept": int(srows.shape[0]),
+                               "gpu_launches": int(launches),
+                               "e2e": {"value": sd.shape[0] / (sems / args.steps) / 1e3, "unit": "Mboxes/s",
+                                       "ms_per_step": sems / args.steps, "h2d_bytes_per_step": int(sd.numel() * 4 + sg.numel() * 4),
+                                       "d2h_bytes_per_step": int(srows.numel() * 4 + scnt.numel() * 8)},
+                               "workload": "Soft-NMS (linear, iou_thr 0.3, min_score 0.05) of the C2 candidates' AABB envelopes, "
+                                           "15 class groups in one launch (one CTA per class); sequential in the selected box, "
+                                           "so latency bound"}
         if not args.no_e2e:
             import numpy as np
             from aidet_b200.ops import batched_rnms
@@ -692,6 +716,35 @@ def cpu_nms_reference_hbb():
     return dets.shape[0] / dt / 1e6, dt
 
 
+def soft_nms_inputs():
+    """C2 candidates as axis-aligned envelopes [x1,y1,x2,y2,score] + class ids (Soft-NMS is an HBB op in the reference)."""
+    import torch
+    from aidet_b200 import synth
+    cb, cs, cg, ng = nms_inputs(dense=False, images=1)
+    p = synth.thetaobb2pointobb(cb).view(-1, 4, 2)
+    hbb = torch.cat([p.min(1)[0], p.max(1)[0]], 1)
+    return torch.cat([hbb, cs[:, None]], 1).contiguous(), cg, ng
+
+
+def cpu_soft_nms_reference():
+    """The reference's own soft_nms_cpu_kernel (nms_cpu.cpp:70-201, oracle/_ref, unmodified), class by class as
+    its Python loops call it (linear, iou_thr 0.3, min_score 0.05)."""
+    from oracle import build_ref
+    mod = build_ref.load()
+    if mod is None:
+        return None
+    dets, cg, ng = soft_nms_inputs()
+    parts = [dets[cg == g].contiguous() for g in range(ng)]
+    mod.soft_nms(parts[0][:16].clone(), 0.3, 1, 0.5, 0.05)
+    t0 = time.perf_counter()
+    kept = 0
+    for d in parts:
+        if d.shape[0]:
+            kept += mod.soft_nms(d.clone(), 0.3, 1, 0.5, 0.05).shape[0]
+    dt = time.perf_counter() - t0
+    return dets.shape[0] / dt / 1e6, dt, kept
+
+
 def cpu_roi(sample_rois=512):
     """float64 oracle rotated RoIAlign fwd + bwd (OpenMP) on the first `sample_rois` RoIs of C3, level by level."""
     import numpy as np
@@ -733,6 +786,11 @@ def cpu_baselines(args):
             out["nms_hbb_reference"] = {"value": ref[0], "unit": "Mboxes/s", "cores": 1, "kind": "reference",
                                         "sample": "reference nms_cpu.cpp (unmodified, oracle/_ref) on the AABB envelopes "
                                                   "of C2, class by class, %.3f s" % ref[1]}
+        sref = cpu_soft_nms_reference()
+        if sref is not None:
+            out["soft_nms_reference"] = {"value": sref[0], "unit": "Mboxes/s", "cores": 1, "kind": "reference", "kept": sref[2],
+                                         "sample": "reference soft_nms_cpu_kernel (nms_cpu.cpp:70-201, unmodified, oracle/_ref) on "
+                                                   "the AABB envelopes of C2, class by class, linear, %.3f s" % sref[1]}
     if args.workload in ("all", "roi"):
         v, dt = cpu_roi(512)
         out["roialign"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
@@ -809,8 +867,12 @@ def main():
         if "iou" in cb:
             line["cpu_baseline"] = cb.pop("iou")
         for k, v in cb.items():
-            tgt = {"nms": "nms", "nms_hbb_reference": "nms", "roialign": "roialign"}[k]
+            tgt = {"nms": "nms", "nms_hbb_reference": "nms", "soft_nms_reference": "nms", "roialign": "roialign"}[k]
             if tgt in line:
+                if k == "soft_nms_reference":
+                    if "soft_nms" in line[tgt]:
+                        line[tgt]["soft_nms"]["cpu_baseline"] = v
+                    continue
                 line[tgt]["cpu_baseline" if k != "nms_hbb_reference" else "cpu_baseline_hbb_reference"] = v
     if D.rank == 0:
         emit(line)

@@ -62,6 +62,26 @@ def test_delta_codecs_roundtrip_and_formulas():
     assert len(res) == 15 and res[0].shape == (0, 6)
 
 
+def test_hobb_codecs():
+    # transforms.py:137-163 written out for one box: first edge (10,20)->(50,20), height 30 -> a = pi/2, corners below it
+    # (x4 = 10 - 30 cos(pi/2) = 9.999999999999998 in double, which the reference's int() truncates to 9, :161)
+    assert core.hobb2pointobb([10, 20, 50, 20, 30]) == [10, 20, 50, 20, 50, 50, 9, 50]
+    t = torch.tensor([[10., 20., 50., 20., 30.], [0., 0., 30., 40., 10.]])
+    p = core.hobb2pointobb(t)
+    assert torch.allclose(p[0], torch.tensor([10., 20., 50., 20., 50., 50., 10., 50.]), atol=1e-4)
+    e = torch.tensor([30., 40.]) / 50.0                       # second box: unit edge (0.6, 0.8); p3 = p2 + h * (-0.8, 0.6)
+    assert torch.allclose(p[1, 4:6], torch.tensor([30. - 8., 40. + 6.]), atol=1e-4)
+    assert torch.allclose(p[1, 6:8], torch.tensor([-8., 6.]), atol=1e-4)
+    side = (p[1, 4:6] - p[1, 2:4])
+    assert abs(float(side @ e)) < 1e-4 and abs(float(side.norm()) - 10) < 1e-4     # perpendicular, length h
+    prop = torch.tensor([[5., 10., 60., 70.]]).repeat(2, 1)
+    d = core.hobb2delta(prop, t, stds=(0.1, 0.1, 0.1, 0.1, 0.2))
+    back = core.delta2hobb(prop, d, stds=(0.1, 0.1, 0.1, 0.1, 0.2))
+    assert torch.allclose(back[:, :4], t[:, :4], atol=1e-3) and torch.allclose(back[:, 4], t[:, 4] + 1, atol=1e-3)   # gh = h + 1 (:539)
+    r = t.clone()
+    assert core.hobb_rescale(r, 2.0, reverse_flag=True) is r and torch.allclose(r, t / 2)
+
+
 @pytest.mark.gpu
 def test_get_det_rbboxes_matches_class_loop(cuda):
     """decode + rescale + one batched launch == the reference-shaped per-class loop with the single-class op."""
