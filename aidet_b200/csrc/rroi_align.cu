@@ -715,9 +715,9 @@ rroi_tap_gen_merged_kernel(GatherLevels lv, int n_levels, int N, const float* __
       w = (off >= 0) ? w * inv_count : 0.f;
     }
     const bool tap_ok = off >= 0;
-    // equal keys <=> same pixel of the same bin; rejected / idle lanes get unique keys
-    const unsigned long long mkey = tap_ok ? (((unsigned long long)(unsigned)off << 8) | (unsigned)(lane / T))
-                                           : (0x8000000000000000ULL | (unsigned)lane);
+    // equal keys <=> same pixel of the same bin (32-bit MATCH: the pixel index of a plane is < 2^26, checked on the
+    // host); rejected / idle lanes get unique keys
+    const unsigned mkey = tap_ok ? (((unsigned)off << 5) | (unsigned)(lane / T)) : (0x80000000u | (unsigned)lane);
     const unsigned m = __match_any_sync(0xffffffffu, mkey);
     const bool f = tap_ok && (lane == __ffs(m) - 1);
     const float ws = group_sum_ordered(m, w);                       // duplicates summed in tap order
@@ -1027,7 +1027,9 @@ int aidet_rroi_align_bwd_gather_f32(const float* grad_out, float* const* grad_fe
   size_t cb = L.cub_bytes;
   unsigned* counts = seg_end;                                      // (n_pix + 1) words
   AIDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n_pix + 1) * 4, s));
-  if (sample_num <= 2 && !g_roi_bwd_unmerged) {
+  long long max_plane = 0;
+  for (int l = 0; l < n_levels; l++) max_plane = max(max_plane, (long long)H_host[l] * W_host[l]);
+  if (sample_num <= 2 && !g_roi_bwd_unmerged && max_plane < (1LL << 26)) {
 #define AIDET_TAPGEN(G_, IDS_)                                                                                   \
   rroi_tap_gen_merged_kernel<G_, IDS_><<<K, 128, 0, s>>>(lv, n_levels, N, rois, roi_fmt, roi_level, ph, pw, variant, \
                                                          keys_in, ids_in, wts, counts)
