@@ -34,6 +34,16 @@ _SIGNATURES = {
                                               C.c_int, C.c_longlong, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "aidet_riou_aligned_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                          C.c_void_p]),
+    "aidet_riou_aligned_grad_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "aidet_assign_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "aidet_max_iou_assign_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                           C.c_float, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.c_int, C.c_void_p]),
+    "aidet_assign_wrt_overlaps_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float,
+                                                C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "aidet_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "aidet_nms_batched_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -43,7 +43,8 @@ AIDET_HD float frcp(float x) { return 1.0f / x; }
 AIDET_HD float fdiv(float a, float b) { return a / b; }
 #endif
 
-enum { MODE_IOU = 0, MODE_IOF = 1 };
+// MODE_IOF divides by the area of the first box (mmdet/core/bbox/geometry.py:70-71), MODE_IOF_B by the second's.
+enum { MODE_IOU = 0, MODE_IOF = 1, MODE_IOF_B = 2 };
 
 // ---------------------------------------------------------------- records
 // theta-OBB, prepared once per box by the prologue kernel (32 B).  The same record serves
@@ -141,7 +142,7 @@ AIDET_HD float rect_inter(const Rect& a, const Rect& b) {
 // the denormal range, so the plain MUFU.RCP (<= 1 ulp) replaces a guarded division.
 AIDET_HD float finish_overlap(float inter, float area_a, float area_b, int mode) {
   inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_b));
-  float den = (mode == MODE_IOF) ? area_a : (area_a + area_b - inter);
+  float den = (mode == MODE_IOF) ? area_a : (mode == MODE_IOF_B) ? area_b : (area_a + area_b - inter);
   return den > 0.0f ? inter * frcp(den) : 0.0f;
 }
 
@@ -165,6 +166,96 @@ AIDET_HD void rect_prepare(const float* box5, Rect* row, Rect* col) {
   Rect r; rect_prepare(box5, &r);
   if (row) *row = r;
   if (col) *col = r;
+}
+
+// ------------------------------------- d(overlap)/d(box parameters), theta-OBB
+//
+// Used by the rotated IoU loss (the rotated counterpart of mmdet/models/losses/iou_loss.py:10-27, whose HBB
+// form gets its gradient from autograd through bbox_overlaps).  By the transport theorem the derivative of
+// the intersection area with respect to a parameter p of box A is the boundary integral, over the parts of
+// A's edges that lie inside B, of the normal velocity of the edge under p:
+//     translation : n                      -> sum over edges of (inside length) * n
+//     w (h)       : 1/2 on the two edges perpendicular to the w (h) axis, 0 on the others
+//     theta       : (p - centre) x n       -> first moment of the inside interval along the edge
+// so everything reduces to clipping A's four edges against B (two slabs in B's frame) -- closed forms of
+// min/max again, exact wherever the overlap is differentiable.
+
+// [t0,t1] = part of the segment p + t d, t in [0,L], inside |x|<=W, |y|<=H (rdx, rdy = 1/d.x, 1/d.y, never 0/inf
+// thanks to the 1e-20 addend of the caller).  Empty -> t1 == t0.
+AIDET_HD void seg_clip(float px, float py, float rdx, float rdy, float L, float W, float H, float* t0, float* t1) {
+  float xa = (-W - px) * rdx, xb = (W - px) * rdx;
+  float ya = (-H - py) * rdy, yb = (H - py) * rdy;
+  float lo = fmaxf(fmaxf(fminf(xa, xb), fminf(ya, yb)), 0.0f);
+  float hi = fminf(fminf(fmaxf(xa, xb), fmaxf(ya, yb)), L);
+  *t0 = lo; *t1 = fmaxf(hi, lo);
+}
+
+// g[0..4] = d area(A ^ B) / d (cx, cy, w, h, theta) of A   (w, h >= 0 as stored in the record)
+AIDET_HD void rect_inter_grad(const Rect& a, const Rect& b, float* g) {
+  const float relx = a.cx - b.cx, rely = a.cy - b.cy;
+  const float rx = fmaf(b.c, relx, b.s * rely);
+  const float ry = fmaf(b.c, rely, -b.s * relx);
+  const float c = fmaf(a.c, b.c, a.s * b.s) + 1e-20f;       // A's axes in B's frame: u = (c, s), v = (-s, c)
+  const float s = fmaf(a.s, b.c, -a.c * b.s) + 1e-20f;
+  const float rc = frcp(c), rs = frcp(s);
+  const float ux = a.W * c, uy = a.W * s, vx = -a.H * s, vy = a.H * c;
+  const float Lu = a.W + a.W, Lv = a.H + a.H;
+  float t0, t1;
+  // edges x_local = +W / -W run along v from y_local = -H
+  seg_clip(rx + ux - vx, ry + uy - vy, -rs, rc, Lv, b.W, b.H, &t0, &t1);
+  const float len_up = t1 - t0, mom_up = len_up * (0.5f * (t0 + t1) - a.H);
+  seg_clip(rx - ux - vx, ry - uy - vy, -rs, rc, Lv, b.W, b.H, &t0, &t1);
+  const float len_um = t1 - t0, mom_um = len_um * (0.5f * (t0 + t1) - a.H);
+  // edges y_local = +H / -H run along u from x_local = -W
+  seg_clip(rx - ux + vx, ry - uy + vy, rc, rs, Lu, b.W, b.H, &t0, &t1);
+  const float len_vp = t1 - t0, mom_vp = len_vp * (0.5f * (t0 + t1) - a.W);
+  seg_clip(rx - ux - vx, ry - uy - vy, rc, rs, Lu, b.W, b.H, &t0, &t1);
+  const float len_vm = t1 - t0, mom_vm = len_vm * (0.5f * (t0 + t1) - a.W);
+  const float du = len_up - len_um, dv = len_vp - len_vm;
+  const float gx = c * du - s * dv, gy = s * du + c * dv;     // in B's frame
+  g[0] = b.c * gx - b.s * gy;                                 // back to the world frame
+  g[1] = b.s * gx + b.c * gy;
+  g[2] = 0.5f * (len_up + len_um);
+  g[3] = 0.5f * (len_vp + len_vm);
+  g[4] = (mom_um - mom_up) + (mom_vp - mom_vm);
+}
+
+// Overlap of two theta-OBBs and its gradient with respect to both boxes' (cx, cy, w, h, theta).
+// a5 / b5: the raw parameters (sign of w, h is honoured: the area uses |w|, |h|).  Returns the overlap.
+AIDET_HD float rect_overlap_grad(const float* a5, const float* b5, int mode, float* ga, float* gb) {
+  Rect a, b;
+  rect_prepare(a5, &a); rect_prepare(b5, &b);
+#pragma unroll
+  for (int k = 0; k < 5; k++) { ga[k] = 0.0f; gb[k] = 0.0f; }
+  float dx = a.cx - b.cx, dy = a.cy - b.cy, r = a.rad + b.rad;
+  if (fmaf(dx, dx, dy * dy) > r * r) return 0.0f;
+  float inter = rect_inter(a, b);
+  inter = fminf(fmaxf(inter, 0.0f), fminf(a.area, b.area));
+  const float wa = a.W + a.W, ha = a.H + a.H, wb = b.W + b.W, hb = b.H + b.H;
+  float ia[5], ib[5];
+  rect_inter_grad(a, b, ia);
+  rect_inter_grad(b, a, ib);
+  // overlap = inter / den:  d = (dI * P - I * dQ) * Rr  with  (P, Q, Rr) per mode
+  //   iou   : den = S - I, S = area_a + area_b  ->  (dI * S - I * dS) / den^2
+  //   iof   : den = area_a                      ->  (dI * area_a - I * d area_a) / area_a^2
+  const float S = a.area + b.area;
+  const float den = (mode == MODE_IOF) ? a.area : (mode == MODE_IOF_B) ? b.area : (S - inter);
+  if (!(den > 0.0f)) return 0.0f;
+  const float rden = 1.0f / den, r2 = rden * rden;
+  const float P = (mode == MODE_IOU) ? S : den;
+  const float qa = (mode == MODE_IOF_B) ? 0.0f : inter;      // weight of d area_a in dQ
+  const float qb = (mode == MODE_IOF) ? 0.0f : inter;        // weight of d area_b
+  const float dAa[5] = {0.0f, 0.0f, ha, wa, 0.0f}, dAb[5] = {0.0f, 0.0f, hb, wb, 0.0f};
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    ga[k] = (ia[k] * P - qa * dAa[k]) * r2;
+    gb[k] = (ib[k] * P - qb * dAb[k]) * r2;
+  }
+  if (a5[2] < 0.0f) ga[2] = -ga[2];
+  if (a5[3] < 0.0f) ga[3] = -ga[3];
+  if (b5[2] < 0.0f) gb[2] = -gb[2];
+  if (b5[3] < 0.0f) gb[3] = -gb[3];
+  return inter * rden;
 }
 
 // --------------------------------------------- quad ^ quad (point-OBB, general)
@@ -268,7 +359,7 @@ AIDET_HD float hbb_overlap(const HbbBox& a, const HbbBox& b, float one, int mode
   float inter = w * h;
   float sa = (a.x2 - a.x1 + one) * (a.y2 - a.y1 + one);
   float sb = (b.x2 - b.x1 + one) * (b.y2 - b.y1 + one);
-  float den = (mode == MODE_IOF) ? sa : (sa + sb - inter);
+  float den = (mode == MODE_IOF) ? sa : (mode == MODE_IOF_B) ? sb : (sa + sb - inter);
   return inter / den;
 }
 

@@ -21,70 +21,9 @@
 
 #include "common.cuh"
 #include "geom.cuh"
+#include "pairop.cuh"
 
 namespace aidet {
-
-struct RectKind {
-  using Row = RectRow; using Col = RectCol;
-  static constexpr int FMT = 5;
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return rect_inter(a, b); }
-  __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { rect_prepare(p, r, c); }
-  template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.cx; }
-  template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.cy; }
-};
-struct QuadKind {
-  using Row = QuadRow; using Col = QuadCol;
-  static constexpr int FMT = 8;
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return quad_inter(a, b); }
-  __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { quad_prepare(p, r, c); }
-  template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.mx; }
-  template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.my; }
-};
-
-// fmt 4: axis-aligned (x1,y1,x2,y2) boxes with the legacy +1 pixel convention of mmdet/core/bbox/geometry.py:57-86
-// (bbox_overlaps) -- the same tiled kernel; this one is bound by the 4 B/pair result store, not by arithmetic.
-struct HbbKind {
-  using Row = HbbBox; using Col = HbbBox;
-  static constexpr int FMT = 4;
-  __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) {
-    HbbBox b{p[0], p[1], p[2], p[3]};
-    if (r) *r = b;
-    if (c) *c = b;
-  }
-};
-
-// Matrix-row boxes are staged as Row records (the box that is transformed), matrix-column
-// boxes live in registers as Col records (the box whose frame is used).
-template <class K>
-struct PairOp {
-  using S = typename K::Row;   // staged (matrix row)
-  using R = typename K::Col;   // registers (matrix col)
-  __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) {
-    float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
-    if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;
-    return finish_overlap(K::inter(s, r), s.area, r.area, mode);
-  }
-};
-
-template <>
-struct PairOp<HbbKind> {
-  using S = HbbBox; using R = HbbBox;
-  __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) { return hbb_overlap(s, r, 1.0f, mode); }
-};
-
-template <class K>
-__global__ void __launch_bounds__(256) riou_prepare_kernel(const float* __restrict__ boxes, int n,
-                                                           typename K::Row* rows, typename K::Col* cols) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float b[K::FMT];
-#pragma unroll
-  for (int k = 0; k < K::FMT; k++) b[k] = boxes[(size_t)i * K::FMT + k];
-  typename K::Row r; typename K::Col c;
-  K::prepare(b, rows ? &r : nullptr, cols ? &c : nullptr);
-  if (rows) rows[i] = r;
-  if (cols) cols[i] = c;
-}
 
 constexpr int kColsPerTile = 256;
 constexpr int kMaxTileRows = 64;
@@ -182,6 +121,28 @@ __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restri
   K::prepare(pa, &r, nullptr);
   K::prepare(pb, nullptr, &c);
   out[i] = PairOp<K>::overlap(r, c, mode);
+}
+
+// d overlap(a[i], b[i]) / d (cx,cy,w,h,theta) of both boxes, scaled by the upstream gradient (theta-OBB only):
+// the backward of the aligned overlap, i.e. of the rotated IoU loss (rotated counterpart of
+// mmdet/models/losses/iou_loss.py:10-27).  One thread per pair; geom.cuh: rect_overlap_grad.
+__global__ void __launch_bounds__(256) riou_aligned_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                int n, int mode, const float* __restrict__ grad_ov,
+                                                                float* __restrict__ ov, float* __restrict__ grad_a,
+                                                                float* __restrict__ grad_b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float pa[5], pb[5], ga[5], gb[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) { pa[k] = a[(size_t)i * 5 + k]; pb[k] = b[(size_t)i * 5 + k]; }
+  float v = rect_overlap_grad(pa, pb, mode, ga, gb);
+  float go = grad_ov ? grad_ov[i] : 1.0f;
+  if (ov) ov[i] = v;
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    if (grad_a) grad_a[(size_t)i * 5 + k] = go * ga[k];
+    if (grad_b) grad_b[(size_t)i * 5 + k] = go * gb[k];
+  }
 }
 
 template <class K>
@@ -312,6 +273,21 @@ int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int m
   if (fmt == 5) riou_aligned_kernel<RectKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
   else if (fmt == 4) riou_aligned_kernel<HbbKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
   else riou_aligned_kernel<QuadKind><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, out);
+  count_launch(1);
+  AIDET_CUDA(cudaGetLastError());
+  return AIDET_OK;
+}
+
+int aidet_riou_aligned_grad_f32(const float* a, const float* b, int n, int fmt, int mode, const float* grad_ov,
+                                float* ov, float* grad_a, float* grad_b, int device, void* stream) {
+  AIDET_REQUIRE(fmt == 5, "aidet_riou_aligned_grad_f32: only theta-OBB (fmt 5) has a gradient, got fmt %d", fmt);
+  AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_aligned_grad_f32: bad mode %d", mode);
+  AIDET_REQUIRE(n >= 0, "aidet_riou_aligned_grad_f32: negative size");
+  if (n == 0) return AIDET_OK;
+  AIDET_REQUIRE(a && b, "aidet_riou_aligned_grad_f32: null pointer");
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  riou_aligned_grad_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, grad_ov, ov, grad_a, grad_b);
   count_launch(1);
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;

@@ -102,6 +102,108 @@ def riou_aligned(a, b, mode="iou"):
     return out
 
 
+def riou_aligned_grad(a, b, grad_ov=None, mode="iou", want_b=True):
+    """Backward of `riou_aligned` for theta-OBB pairs: (ov (n,), grad_a (n,5), grad_b (n,5) | None), the gradients
+    scaled by `grad_ov` (n,) when given.  aidet_riou_aligned_grad_f32."""
+    assert mode in ("iou", "iof")
+    a, b = _f32c(a, 5, "a"), _f32c(b, 5, "b")
+    if a.shape != b.shape:
+        raise ValueError("aligned overlaps need equal shapes, got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+    n = a.size(0)
+    ov = torch.empty((n,), dtype=torch.float32, device=a.device)
+    ga = torch.empty((n, 5), dtype=torch.float32, device=a.device)
+    gb = torch.empty((n, 5), dtype=torch.float32, device=a.device) if want_b else None
+    if n == 0:
+        return ov, ga, gb
+    if grad_ov is not None:
+        L.require_cuda(grad_ov, "grad_ov")
+        grad_ov = grad_ov.float().contiguous().view(-1)
+        assert grad_ov.numel() == n
+    dev = a.device.index
+    with torch.cuda.device(dev):
+        L.check(L.lib().aidet_riou_aligned_grad_f32(L.dptr(a), L.dptr(b), n, 5,
+                                                    L.MODE_IOF if mode == "iof" else L.MODE_IOU, L.dptr(grad_ov),
+                                                    L.dptr(ov), L.dptr(ga), L.dptr(gb), dev, L.stream_ptr(dev)),
+                "aidet_riou_aligned_grad_f32")
+    return ov, ga, gb
+
+
+def _neg_bounds(neg_iou_thr):
+    """(lo, hi) of max_iou_assigner.py:161-167: a float thr means [0, thr), a pair [thr[0], thr[1]), else none."""
+    if isinstance(neg_iou_thr, float):
+        return 0.0, neg_iou_thr
+    if isinstance(neg_iou_thr, tuple):
+        assert len(neg_iou_thr) == 2
+        return float(neg_iou_thr[0]), float(neg_iou_thr[1])
+    return float("inf"), float("inf")
+
+
+def max_iou_assign(gts, bboxes, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0, gt_max_assign_all=True, gt_ignore=None,
+                   ignore_iof_thr=-1.0, ignore_wrt_candidates=True, gt_labels=None):
+    """Fused overlap + MaxIoUAssigner steps (aidet_max_iou_assign_f32).  gts (k,fmt), bboxes (n,fmt), k, n >= 1,
+    fmt 4 | 5 | 8.  -> (gt_inds (n,) int64, max_overlaps (n,) float32, labels (n,) int64 | None)."""
+    fmt = bboxes.size(-1)
+    gts, bboxes = _f32c(gts, fmt, "gt_bboxes"), _f32c(bboxes, fmt, "bboxes")
+    k, n = gts.size(0), bboxes.size(0)
+    assert k > 0 and n > 0
+    k_ign = 0
+    if gt_ignore is not None and gt_ignore.numel() > 0 and ignore_iof_thr > 0:
+        gt_ignore = _f32c(gt_ignore, fmt, "gt_bboxes_ignore")
+        k_ign = gt_ignore.size(0)
+    else:
+        gt_ignore = None
+    if gt_labels is not None:
+        L.require_cuda(gt_labels, "gt_labels")
+        gt_labels = gt_labels.long().contiguous()
+        assert gt_labels.numel() == k
+    dev = bboxes.device
+    gt_inds = torch.empty((n,), dtype=torch.long, device=dev)
+    max_ov = torch.empty((n,), dtype=torch.float32, device=dev)
+    labels = torch.empty((n,), dtype=torch.long, device=dev) if gt_labels is not None else None
+    lo, hi = _neg_bounds(neg_iou_thr)
+    lib = L.lib()
+    ws_bytes = lib.aidet_assign_workspace_bytes(k, n, k_ign, fmt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev.index):
+        L.check(lib.aidet_max_iou_assign_f32(L.dptr(gts), k, L.dptr(bboxes), n, fmt, L.dptr(gt_ignore), k_ign,
+                                             float(ignore_iof_thr), int(bool(ignore_wrt_candidates)),
+                                             float(pos_iou_thr), lo, hi, float(min_pos_iou),
+                                             int(bool(gt_max_assign_all)), L.dptr(gt_labels), L.dptr(gt_inds),
+                                             L.dptr(max_ov), L.dptr(labels), L.dptr(ws), ws_bytes, dev.index,
+                                             L.stream_ptr(dev.index)), "aidet_max_iou_assign_f32")
+    return gt_inds, max_ov, labels
+
+
+def assign_wrt_overlaps(overlaps, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0, gt_max_assign_all=True, gt_labels=None):
+    """MaxIoUAssigner steps on a given (k, n) overlap matrix, k, n >= 1 (aidet_assign_wrt_overlaps_f32)."""
+    L.require_cuda(overlaps, "overlaps")
+    assert overlaps.dim() == 2
+    ov = overlaps.float()
+    if ov.stride(1) != 1:
+        ov = ov.contiguous()
+    k, n = ov.shape
+    assert k > 0 and n > 0
+    if gt_labels is not None:
+        L.require_cuda(gt_labels, "gt_labels")
+        gt_labels = gt_labels.long().contiguous()
+        assert gt_labels.numel() == k
+    dev = ov.device
+    gt_inds = torch.empty((n,), dtype=torch.long, device=dev)
+    max_ov = torch.empty((n,), dtype=torch.float32, device=dev)
+    labels = torch.empty((n,), dtype=torch.long, device=dev) if gt_labels is not None else None
+    lo, hi = _neg_bounds(neg_iou_thr)
+    lib = L.lib()
+    ws_bytes = lib.aidet_assign_workspace_bytes(k, n, 0, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev.index):
+        L.check(lib.aidet_assign_wrt_overlaps_f32(L.dptr(ov), k, n, ov.stride(0), float(pos_iou_thr), lo, hi,
+                                                  float(min_pos_iou), int(bool(gt_max_assign_all)),
+                                                  L.dptr(gt_labels), L.dptr(gt_inds), L.dptr(max_ov), L.dptr(labels),
+                                                  L.dptr(ws), ws_bytes, dev.index, L.stream_ptr(dev.index)),
+                "aidet_assign_wrt_overlaps_f32")
+    return gt_inds, max_ov, labels
+
+
 _THR_CACHE = {}
 
 

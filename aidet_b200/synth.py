@@ -54,6 +54,41 @@ def dota_boxes(n, side=1024, seed=0, dense=False):
     return boxes, scores.float()
 
 
+def regression_pairs(n, side=1024, seed=0, shift=0.15, scale=0.35, dtheta=0.3):
+    """(pred, target) aligned (n,5) theta-OBB pairs as a box-regression loss sees them: targets are DOTA-shaped
+    boxes, predictions the same boxes with the centre moved by N(0, shift * sqrt(w h)), sides scaled by
+    U(1 - scale, 1 + scale) and the angle turned by N(0, dtheta) -- so nearly every pair overlaps."""
+    target, _ = dota_boxes(n, side=side, seed=seed)
+    g = _gen(seed + 7919)
+    t = target.double()
+    size = torch.sqrt(t[:, 2] * t[:, 3])
+    d = torch.randn(n, 2, generator=g, dtype=torch.float64) * (shift * size)[:, None]
+    sc = _uniform(g, 2 * n, 1 - scale, 1 + scale).view(n, 2)
+    dth = torch.randn(n, generator=g, dtype=torch.float64) * dtheta
+    pred = torch.stack([t[:, 0] + d[:, 0], t[:, 1] + d[:, 1], t[:, 2] * sc[:, 0], t[:, 3] * sc[:, 1], t[:, 4] + dth], 1)
+    return pred.float(), target
+
+
+def assign_case(n_boxes, n_gts, side=1024, seed=0, n_ignore=0):
+    """(bboxes (n,5), gt (k,5), gt_ignore (q,5), gt_labels (k,)): truths are DOTA-shaped boxes, candidates a mix of
+    jittered copies of truths (positives of every quality, exact duplicates included so that a truth's best
+    overlap is tied between candidates) and unrelated DOTA-shaped boxes (negatives)."""
+    gt, _ = dota_boxes(n_gts, side=side, seed=seed)
+    ign, _ = dota_boxes(max(n_ignore, 1), side=side, seed=seed + 1)
+    bg, _ = dota_boxes(n_boxes, side=side, seed=seed + 2)
+    g = _gen(seed + 104729)
+    n_pos = n_boxes // 3
+    src = torch.randint(0, n_gts, (n_pos,), generator=g)
+    pos, _ = regression_pairs(n_gts, side=side, seed=seed)          # jittered versions of the same truths
+    q = _uniform(g, n_pos, 0, 1)[:, None].float()
+    boxes = bg.clone()
+    boxes[:n_pos] = gt[src] * (1 - q) + pos[src] * q                 # from exact copies (q=0) to loose matches
+    n_dup = min(8, n_pos // 2)
+    boxes[n_pos:n_pos + n_dup] = boxes[:n_dup]                       # exact duplicates -> tied maxima
+    labels = torch.randint(1, 16, (n_gts,), generator=g)
+    return boxes, gt, ign[:n_ignore], labels
+
+
 def thetaobb2pointobb(boxes):
     """(n,5) -> (n,8) in cv2.boxPoints order (mmdet/core/rbbox/transforms.py:45-55), float64 math."""
     b = boxes.double()

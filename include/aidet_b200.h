@@ -83,6 +83,37 @@ int aidet_riou_matrix_mcast_f32(const float* a, int m, const float* b, int n, in
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out,
                            int device, void* stream);
 
+/* Backward of the aligned overlap for theta-OBB pairs (fmt must be 5): grad_a[i] = grad_ov[i] * d ovr(a[i], b[i]) /
+ * d (cx,cy,w,h,theta of a[i]), likewise grad_b; grad_ov NULL = ones; ov (n), grad_a (n,5), grad_b (n,5) may each be
+ * NULL.  This is what makes the rotated IoU loss trainable -- the rotated counterpart of iou_loss
+ * (mmdet/models/losses/iou_loss.py:10-27), which gets its gradient from autograd through bbox_overlaps. */
+int aidet_riou_aligned_grad_f32(const float* a, const float* b, int n, int fmt, int mode, const float* grad_ov,
+                                float* ov, float* grad_a, float* grad_b, int device, void* stream);
+
+/* ---- max-IoU assignment fused with the overlap computation -----------------
+ * Replaces: MaxIoUAssigner.assign / assign_wrt_overlaps (mmdet/core/bbox/assigners/max_iou_assigner.py:52-195):
+ * overlap matrix + max/argmax along both axes + a Python loop over the ground truths.  The (m, n) matrix is never
+ * materialised (two passes that recompute the overlaps; see csrc/riou_assign.cu).
+ *   gts (m,fmt), bboxes (n,fmt), fmt 4 (HBB, +1 convention = bbox_overlaps), 5 or 8; m, n >= 1
+ *   gt_ignore (k_ign,fmt) or NULL/0: boxes whose IoF with any ignore box exceeds ignore_iof_thr (> 0) count as -1
+ *     (:104-113); ignore_wrt_candidates != 0 -> IoF over the box's own area, else over the ignore box's
+ *   negatives: neg_lo <= max_overlap < neg_hi (:161-167: a float thr is (0, thr); pass neg_lo = +inf for none)
+ *   gt_max_assign_all: :178-182
+ *   gt_labels (m) int64 or NULL; outputs gt_inds (n) int64 in {-1, 0, 1..m}, max_overlaps (n), labels (n) int64 or NULL
+ * Ties along the gt axis resolve to the FIRST gt (the CPU behaviour of Tensor.max(dim=0)). */
+size_t aidet_assign_workspace_bytes(int m, int n, int k_ign, int fmt);
+int aidet_max_iou_assign_f32(const float* gts, int m, const float* bboxes, int n, int fmt, const float* gt_ignore,
+                             int k_ign, float ignore_iof_thr, int ignore_wrt_candidates, float pos_iou_thr,
+                             float neg_lo, float neg_hi, float min_pos_iou, int gt_max_assign_all,
+                             const long long* gt_labels, long long* gt_inds, float* max_overlaps, long long* labels,
+                             void* workspace, size_t ws_bytes, int device, void* stream);
+/* Same assignment from a caller-provided (m, n) overlap matrix (row stride ld elements; entries >= 0, or -1 for
+ * "ignored"): assign_wrt_overlaps (:122-195).  workspace >= aidet_assign_workspace_bytes(m, n, 0, 0). */
+int aidet_assign_wrt_overlaps_f32(const float* overlaps, int m, int n, long long ld, float pos_iou_thr, float neg_lo,
+                                  float neg_hi, float min_pos_iou, int gt_max_assign_all, const long long* gt_labels,
+                                  long long* gt_inds, float* max_overlaps, long long* labels, void* workspace,
+                                  size_t ws_bytes, int device, void* stream);
+
 /* ---- batched NMS (rotated and axis-aligned) -------------------------------
  * Replaces: nms_cuda.nms (mmdet/ops/nms/src/nms_kernel.cu:71-139: sort, 64x64 bitmask
  * tiles, D2H mask copy, host scan) and the per-class Python loops of

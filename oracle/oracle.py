@@ -38,6 +38,7 @@ def lib():
         build()
         _lib = C.CDLL(_SO)
         _lib.oracle_riou_pair.restype = C.c_double
+        _lib.oracle_riou_pair_d.restype = C.c_double
         _lib.oracle_nms.restype = C.c_int
         _lib.oracle_nms_verify.restype = C.c_int
     return _lib
@@ -78,6 +79,19 @@ def riou_aligned(a, b, mode="iou", algo=ALGO_SH):
     lib().oracle_riou_aligned(_p(a), _p(b), C.c_int(a.shape[0]), C.c_int(fmt),
                               C.c_int(MODE_IOF if mode == "iof" else MODE_IOU), C.c_int(algo), _p(out))
     return out
+
+
+def riou_aligned_grad_fd(a, b, mode="iou", step=1e-6):
+    """theta-OBB pairs in float64 -> (overlap (n,), central-difference gradient (n,10) w.r.t. a's then b's
+    (cx,cy,w,h,theta)).  The checker for the analytic gradient of the rotated IoU loss."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, 5))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1, 5))
+    assert a.shape == b.shape
+    ov = np.empty((a.shape[0],), np.float64)
+    grad = np.empty((a.shape[0], 10), np.float64)
+    lib().oracle_riou_aligned_grad_fd(_p(a), _p(b), C.c_int(a.shape[0]), C.c_int({"iou": 0, "iof": 1, "iof_b": 2}[mode]),
+                                      C.c_double(step), _p(ov), _p(grad))
+    return ov, grad
 
 
 def hbb_overlaps(a, b, mode="iou", plus_one=True):
@@ -161,3 +175,55 @@ def map_roi_levels(rois5, finest_scale=56, num_levels=4):
     out = np.empty((r.shape[0],), np.int32)
     lib().oracle_map_roi_levels(_p(r), C.c_int(r.shape[0]), C.c_double(finest_scale), C.c_int(num_levels), _p(out))
     return out
+
+
+def max_iou_assign_wrt_overlaps(overlaps, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0, gt_max_assign_all=True,
+                                gt_labels=None):
+    """numpy restatement of MaxIoUAssigner.assign_wrt_overlaps
+    (mmdet/core/bbox/assigners/max_iou_assigner.py:122-195), step by step; pinned to outputs of the reference's own
+    class in tests/golden/golden_assign_v1.npz.  overlaps (k, n), -1 entries = ignored.
+    -> (gt_inds (n,) int64, max_overlaps (n,), labels (n,) int64 | None)"""
+    ov = np.asarray(overlaps)
+    k, n = ov.shape
+    gt_inds = np.full((n,), -1, np.int64)                                   # :137-139
+    if k == 0 or n == 0:                                                    # :141-153
+        if k == 0:
+            gt_inds[:] = 0
+        return gt_inds, np.zeros((n,), ov.dtype), (None if gt_labels is None else np.zeros((n,), np.int64))
+    max_ov, argmax_ov = ov.max(0), ov.argmax(0)                             # :155  (first index on ties)
+    gt_max, gt_argmax = ov.max(1), ov.argmax(1)                             # :158
+    if isinstance(neg_iou_thr, float):                                      # :161-163
+        gt_inds[(max_ov >= 0) & (max_ov < neg_iou_thr)] = 0
+    elif isinstance(neg_iou_thr, tuple):                                    # :164-167
+        gt_inds[(max_ov >= neg_iou_thr[0]) & (max_ov < neg_iou_thr[1])] = 0
+    pos = max_ov >= pos_iou_thr                                             # :170-171
+    gt_inds[pos] = argmax_ov[pos] + 1
+    for i in range(k):                                                      # :174-182
+        if gt_max[i] >= min_pos_iou:
+            if gt_max_assign_all:
+                gt_inds[ov[i, :] == gt_max[i]] = i + 1
+            else:
+                gt_inds[gt_argmax[i]] = i + 1
+    labels = None
+    if gt_labels is not None:                                               # :184-190
+        labels = np.zeros((n,), np.int64)
+        p = gt_inds > 0
+        labels[p] = np.asarray(gt_labels)[gt_inds[p] - 1]
+    return gt_inds, max_ov, labels
+
+
+def max_iou_assign(bboxes, gt_bboxes, pos_iou_thr, neg_iou_thr, min_pos_iou=0.0, gt_max_assign_all=True,
+                   ignore_iof_thr=-1, ignore_wrt_candidates=True, gt_bboxes_ignore=None, gt_labels=None):
+    """MaxIoUAssigner.assign (max_iou_assigner.py:99-120) on the float64 oracle overlaps; boxes (n,4|5|8)."""
+    b, g = np.asarray(bboxes, np.float32), np.asarray(gt_bboxes, np.float32)
+    fmt = g.shape[-1]
+    over = (lambda x, y, mode="iou": hbb_overlaps(x, y, mode)) if fmt == 4 else (lambda x, y, mode="iou": riou_matrix(x, y, mode))
+    ov = over(g, b)                                                         # :102
+    if ignore_iof_thr > 0 and gt_bboxes_ignore is not None and len(gt_bboxes_ignore) and len(b):   # :104-113
+        ig = np.asarray(gt_bboxes_ignore, np.float32)
+        if ignore_wrt_candidates:
+            ign_max = over(b, ig, "iof").max(1)
+        else:
+            ign_max = over(ig, b, "iof").max(0)
+        ov[:, ign_max > ignore_iof_thr] = -1
+    return max_iou_assign_wrt_overlaps(ov, pos_iou_thr, neg_iou_thr, min_pos_iou, gt_max_assign_all, gt_labels)

@@ -189,6 +189,42 @@ double oracle_riou_pair(const float* a, const float* b, int fmt, int mode, int a
   return pair_overlap(qa, qb, mode, algo);
 }
 
+/* theta-OBB pair with DOUBLE parameters (cx,cy,w,h,theta): lets tests/ take central finite differences of the
+ * overlap (step 1e-6 px) as the checker for the analytic gradient of the rotated IoU loss
+ * (rotated counterpart of mmdet/models/losses/iou_loss.py:10-27).  mode 2 = inter / area_b. */
+static void thetaobb_to_quad_d(const double* b, pt* q) {
+  double cx = b[0], cy = b[1], w = fabs(b[2]), h = fabs(b[3]);
+  double c = cos(b[4]) * 0.5, s = sin(b[4]) * 0.5;
+  q[0].x = cx - s * h - c * w; q[0].y = cy + c * h - s * w;
+  q[1].x = cx + s * h - c * w; q[1].y = cy - c * h - s * w;
+  q[2].x = 2 * cx - q[0].x;    q[2].y = 2 * cy - q[0].y;
+  q[3].x = 2 * cx - q[1].x;    q[3].y = 2 * cy - q[1].y;
+}
+
+double oracle_riou_pair_d(const double* a, const double* b, int mode, int algo) {
+  pt qa[4], qb[4]; thetaobb_to_quad_d(a, qa); thetaobb_to_quad_d(b, qb);
+  if (mode == 2) return pair_overlap(qb, qa, 1, algo);
+  return pair_overlap(qa, qb, mode, algo);
+}
+
+/* central differences of oracle_riou_pair_d: grad (n,10) = d ov / d (a params, b params) */
+void oracle_riou_aligned_grad_fd(const double* a, const double* b, int n, int mode, double step, double* ov,
+                                 double* grad) {
+#pragma omp parallel for
+  for (int i = 0; i < n; i++) {
+    double p[10];
+    for (int k = 0; k < 5; k++) { p[k] = a[5 * (size_t)i + k]; p[5 + k] = b[5 * (size_t)i + k]; }
+    ov[i] = oracle_riou_pair_d(p, p + 5, mode, 0);
+    for (int k = 0; k < 10; k++) {
+      double keep = p[k];
+      p[k] = keep + step; double fp = oracle_riou_pair_d(p, p + 5, mode, 0);
+      p[k] = keep - step; double fm = oracle_riou_pair_d(p, p + 5, mode, 0);
+      p[k] = keep;
+      grad[10 * (size_t)i + k] = (fp - fm) / (2 * step);
+    }
+  }
+}
+
 void oracle_riou_matrix(const float* a, int m, const float* b, int n, int fmt, int mode, int algo,
                         double* out) {
   pt* qb = (pt*)malloc(sizeof(pt) * 4 * (size_t)(n > 0 ? n : 1));

@@ -27,3 +27,9 @@ extern "C" void sim_riou_matrix(const float* a, int m, const float* b, int n, in
     }
   }
 }
+
+// mirrors riou_aligned_grad_kernel of riou.cu (theta-OBB): out (n), grad (n,10) = d ov / d (a, b)
+extern "C" void sim_riou_aligned_grad(const float* a, const float* b, int n, int mode, float* out, float* grad) {
+  for (int i = 0; i < n; i++)
+    out[i] = rect_overlap_grad(a + 5 * (size_t)i, b + 5 * (size_t)i, mode, grad + 10 * (size_t)i, grad + 10 * (size_t)i + 5);
+}

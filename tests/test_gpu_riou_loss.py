@@ -1,0 +1,88 @@
+"""GPU: rotated IoU loss (aidet_riou_aligned_grad_f32 through RotatedIoULoss / rotated_iou) against central
+differences of the float64 oracle overlap, plus the reduction / weight contract of iou_loss.py:129-165."""
+import numpy as np
+import pytest
+import torch
+
+from aidet_b200 import synth
+from aidet_b200.models import RotatedIoULoss, riou_loss, rotated_iou
+from aidet_b200.ops import functional as F
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["iou", "iof"])
+def test_gradient_vs_finite_differences(cuda, mode):
+    pred, target = synth.regression_pairs(20000, seed=11)
+    ov, ga, gb = F.riou_aligned_grad(pred.to(cuda), target.to(cuda), None, mode)
+    ref, fd = O.riou_aligned_grad_fd(pred.numpy(), target.numpy(), mode, 1e-5)
+    _, fd2 = O.riou_aligned_grad_fd(pred.numpy(), target.numpy(), mode, 2e-5)
+    smooth = np.abs(fd - fd2).max(1) < 1e-6                  # pairs on a kink of the overlap are excluded
+    assert smooth.mean() > 0.99
+    assert np.abs(ov.cpu().numpy() - ref).max() <= 1e-5      # BASELINE.json: IoU within 1e-5 absolute
+    g = torch.cat([ga, gb], 1).cpu().numpy().astype(np.float64)
+    err = np.abs(g - fd)[smooth]
+    assert err.max() < 2e-5, err.max()
+    # forward of the gradient kernel == the aligned kernel
+    assert torch.equal(ov, F.riou_aligned(pred.to(cuda), target.to(cuda), mode))
+
+
+def test_loss_backward_and_reductions(cuda):
+    pred, target = synth.regression_pairs(3000, seed=12)
+    p = pred.to(cuda).requires_grad_(True)
+    t = target.to(cuda)
+    loss = riou_loss(p, t, reduction='none')
+    ref, fd = O.riou_aligned_grad_fd(pred.numpy(), target.numpy(), "iou", 1e-5)
+    _, fd2 = O.riou_aligned_grad_fd(pred.numpy(), target.numpy(), "iou", 2e-5)
+    smooth = (np.abs(fd - fd2).max(1) < 1e-6) & (ref > 1e-3)
+    want = -np.log(np.maximum(ref, 1e-6))
+    assert np.abs(loss.detach().cpu().numpy() - want)[ref > 1e-3].max() < 1e-3
+    w = torch.rand(3000, device=cuda)
+    (loss * w).sum().backward()
+    want_g = -(w.cpu().numpy() / np.maximum(ref, 1e-6))[:, None] * fd[:, :5]
+    got = p.grad.cpu().numpy()
+    rel = np.abs(got - want_g)[smooth] / (np.abs(want_g)[smooth].max() + 1e-12)
+    assert np.abs(got - want_g)[smooth].max() < 1e-3 * max(1.0, np.abs(want_g)[smooth].max()), rel.max()
+    # pairs below eps get no gradient (clamp), disjoint pairs stay finite
+    far = t.clone()
+    far[:, 0] += 5000
+    p2 = pred.to(cuda).requires_grad_(True)
+    l2 = riou_loss(p2, far, reduction='sum')
+    l2.backward()
+    assert torch.isfinite(l2) and float(p2.grad.abs().max()) == 0.0
+    assert abs(float(l2) / 3000 + np.log(1e-6)) < 1e-4
+
+    m = RotatedIoULoss(loss_weight=2.0)
+    base = riou_loss(p.detach(), t, reduction='none')
+    assert torch.allclose(m(p.detach(), t), 2.0 * base.mean())
+    assert torch.allclose(m(p.detach(), t, weight=w, avg_factor=100.0), 2.0 * (base * w).sum() / 100.0)
+    assert torch.allclose(m(p.detach(), t, reduction_override='sum'), 2.0 * base.sum())
+    assert m(p.detach(), t, reduction_override='none').shape == (3000,)
+    assert float(m(p, t, weight=torch.zeros(3000, 1, device=cuda))) == 0.0
+
+
+def test_target_gradient_and_descent(cuda):
+    """Both inputs get gradients; gradient descent on the loss increases the IoU (end-to-end sanity of the sign)."""
+    pred, target = synth.regression_pairs(512, seed=13)
+    p = pred.to(cuda).requires_grad_(True)
+    t = target.to(cuda).requires_grad_(True)
+    iou0 = rotated_iou(p, t)
+    iou0.sum().backward()
+    assert p.grad is not None and t.grad is not None
+    assert float((p.grad[:, :2] + t.grad[:, :2]).abs().max()) < 1e-4          # translation invariance
+    x = pred.to(cuda).clone().requires_grad_(True)
+    opt = torch.optim.SGD([x], lr=1.0)
+    first = None
+    for _ in range(60):
+        opt.zero_grad()
+        iou = rotated_iou(x, target.to(cuda))
+        loss = (1 - iou).sum()
+        if first is None:
+            first = float(iou.mean())
+        loss.backward()
+        with torch.no_grad():                 # normalise the step per parameter scale (px vs rad)
+            x.grad[:, :4] *= 50.0
+            x.grad[:, 4] *= 0.05
+        opt.step()
+    assert float(rotated_iou(x, target.to(cuda)).mean()) > first + 0.15
