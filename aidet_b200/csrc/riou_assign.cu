@@ -10,7 +10,8 @@
 //            running (max, first argmax) of its column; row maxima are reduced with redux.sync per warp, then in
 //            shared memory per CTA, then one atomicMax per (CTA, row).  Column results of different row tiles are
 //            combined with a 64-bit atomicMax on (overlap bits, ~row) so ties resolve to the first gt (:155).
-//   pass 2 : the overlaps are RECOMPUTED (identical code, identical bits) and compared with the row maxima:
+//   pass 2 : the overlaps are RECOMPUTED by the SAME kernel (the pass is a run-time argument, so both passes run the
+//            very same SASS and produce identical bits) and compared with the row maxima:
 //            per box the last gt i with overlaps[i, j] == gt_max[i] >= min_pos_iou (:176-180, later gts overwrite
 //            earlier ones), per gt the first such box (:182 when gt_max_assign_all is false).
 //   finish : steps 1-4 of :136-182 per box, labels gathered (:184-190).
@@ -41,11 +42,11 @@ __host__ __device__ __forceinline__ unsigned ov_enc(float v) {
 }
 __device__ __forceinline__ float ov_dec(unsigned e) { return e ? __uint_as_float(e - 1u) : -1.0f; }
 
-template <class K, int MODE, int PASS, bool FROM_MATRIX>
+template <class K, int MODE, bool FROM_MATRIX>
 __global__ void __launch_bounds__(kACols)
 assign_pass_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
                    const typename PairOp<K>::R* __restrict__ cols, int n,
-                   const float* __restrict__ ov_mat, long long ld, int tile_rows,
+                   const float* __restrict__ ov_mat, long long ld, int tile_rows, int PASS,
                    const unsigned long long* __restrict__ ign_best, unsigned ign_thr_enc,
                    unsigned long long* __restrict__ col_best, unsigned* __restrict__ row_e,
                    float min_pos, int* __restrict__ col_last, int* __restrict__ row_first) {
@@ -184,15 +185,15 @@ struct AssignParams {
   const long long* gt_labels; long long* gt_inds; float* max_ov; long long* labels;
 };
 
-template <class K, int MODE, int PASS>
-static void launch_pass(const void* rows, int m, const void* cols, int n, int device, cudaStream_t s,
+template <class K, int MODE>
+static void launch_pass(int pass, const void* rows, int m, const void* cols, int n, int device, cudaStream_t s,
                         const unsigned long long* ign_best, unsigned ign_thr_enc, unsigned long long* col_best,
                         unsigned* row_e, float min_pos, int* col_last, int* row_first) {
   using P = PairOp<K>;
   const int tile_rows = pick_tile_rows(m, n, device);
   dim3 grid(ceil_div(n, kACols), ceil_div(m, tile_rows));
-  assign_pass_kernel<K, MODE, PASS, false><<<grid, kACols, 0, s>>>(
-      (const typename P::S*)rows, m, (const typename P::R*)cols, n, nullptr, 0, tile_rows, ign_best, ign_thr_enc,
+  assign_pass_kernel<K, MODE, false><<<grid, kACols, 0, s>>>(
+      (const typename P::S*)rows, m, (const typename P::R*)cols, n, nullptr, 0, tile_rows, pass, ign_best, ign_thr_enc,
       col_best, row_e, min_pos, col_last, row_first);
   count_launch(1);
 }
@@ -212,17 +213,47 @@ static int assign_tail(const AssignWs& w, int m, int n, const unsigned long long
   return AIDET_OK;
 }
 
-static int assign_clear(const AssignWs& w, int m, int n, int k_ign, cudaStream_t s) {
-  AIDET_CUDA(cudaMemsetAsync(w.col_best, 0, (size_t)n * 8, s));
-  AIDET_CUDA(cudaMemsetAsync(w.row_e, 0, (size_t)m * 4, s));
-  AIDET_CUDA(cudaMemsetAsync(w.col_last, 0xff, (size_t)n * 4, s));     // -1
-  AIDET_CUDA(cudaMemsetAsync(w.row_first, 0x7f, (size_t)m * 4, s));    // 0x7f7f7f7f: beyond any column
-  AIDET_CUDA(cudaMemsetAsync(w.col_sel, 0xff, (size_t)n * 4, s));
-  if (k_ign) {
-    AIDET_CUDA(cudaMemsetAsync(w.ign_best, 0, (size_t)n * 8, s));
-    AIDET_CUDA(cudaMemsetAsync(w.ign_row_e, 0, (size_t)k_ign * 4, s));
+// One launch: prepared records of the truths (rows), the ignore boxes (rows) and the candidates (cols), plus the
+// initial values of every accumulator the passes combine into with atomics.
+template <class K>
+__global__ void __launch_bounds__(256)
+assign_prepare_kernel(const float* __restrict__ gts, int m, const float* __restrict__ ign, int k_ign,
+                      const float* __restrict__ boxes, int n, typename K::Row* rows, typename K::Row* ign_rows,
+                      typename K::Col* cols, AssignWs w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float b[K::FMT];
+  if (i < m) {
+#pragma unroll
+    for (int k = 0; k < K::FMT; k++) b[k] = gts[(size_t)i * K::FMT + k];
+    typename K::Row r; K::prepare(b, &r, nullptr);
+    rows[i] = r;
+    w.row_e[i] = 0u; w.row_first[i] = INT_MAX;
+    return;
   }
-  return AIDET_OK;
+  i -= m;
+  if (i < k_ign) {
+#pragma unroll
+    for (int k = 0; k < K::FMT; k++) b[k] = ign[(size_t)i * K::FMT + k];
+    typename K::Row r; K::prepare(b, &r, nullptr);
+    ign_rows[i] = r;
+    w.ign_row_e[i] = 0u;
+    return;
+  }
+  i -= k_ign;
+  if (i < n) {
+#pragma unroll
+    for (int k = 0; k < K::FMT; k++) b[k] = boxes[(size_t)i * K::FMT + k];
+    typename K::Col c; K::prepare(b, nullptr, &c);
+    cols[i] = c;
+    w.col_best[i] = 0ull; w.col_last[i] = -1; w.col_sel[i] = -1;
+    if (k_ign) w.ign_best[i] = 0ull;
+  }
+}
+
+__global__ void __launch_bounds__(256) assign_init_kernel(int m, int n, AssignWs w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) { w.row_e[i] = 0u; w.row_first[i] = INT_MAX; }
+  if (i < n) { w.col_best[i] = 0ull; w.col_last[i] = -1; w.col_sel[i] = -1; }
 }
 
 template <class K>
@@ -231,28 +262,25 @@ static int assign_fused(const float* gts, int m, const float* boxes, int n, cons
                         cudaStream_t s) {
   using P = PairOp<K>;
   AssignWs w = assign_layout(ws, m, n, k_ign, K::FMT);
-  if (int rc = assign_clear(w, m, n, k_ign, s)) return rc;
-  riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(gts, m, (typename K::Row*)w.rows, nullptr);
-  riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(boxes, n, nullptr, (typename K::Col*)w.cols);
-  count_launch(2);
+  assign_prepare_kernel<K><<<ceil_div(m + k_ign + n, 256), 256, 0, s>>>(
+      gts, m, gt_ignore, k_ign, boxes, n, (typename K::Row*)w.rows, (typename K::Row*)w.ign_rows, (typename K::Col*)w.cols, w);
+  count_launch(1);
   const unsigned long long* ign_best = nullptr;
   unsigned ign_thr_enc = 0;
   if (k_ign) {
-    riou_prepare_kernel<K><<<ceil_div(k_ign, 256), 256, 0, s>>>(gt_ignore, k_ign, (typename K::Row*)w.ign_rows, nullptr);
-    count_launch(1);
     // iof(bboxes, gt_ignore) divides by the box (column) area, iof(gt_ignore, bboxes) by the ignore (row) area
     if (wrt_candidates)
-      launch_pass<K, MODE_IOF_B, 1>(w.ign_rows, k_ign, w.cols, n, device, s, nullptr, 0, w.ign_best, w.ign_row_e, 0.f,
+      launch_pass<K, MODE_IOF_B>(1, w.ign_rows, k_ign, w.cols, n, device, s, nullptr, 0, w.ign_best, w.ign_row_e, 0.f,
                                     nullptr, nullptr);
     else
-      launch_pass<K, MODE_IOF, 1>(w.ign_rows, k_ign, w.cols, n, device, s, nullptr, 0, w.ign_best, w.ign_row_e, 0.f,
+      launch_pass<K, MODE_IOF>(1, w.ign_rows, k_ign, w.cols, n, device, s, nullptr, 0, w.ign_best, w.ign_row_e, 0.f,
                                   nullptr, nullptr);
     ign_best = w.ign_best;
     ign_thr_enc = ov_enc(ign_thr);
   }
-  launch_pass<K, MODE_IOU, 1>(w.rows, m, w.cols, n, device, s, ign_best, ign_thr_enc, w.col_best, w.row_e, 0.f, nullptr,
+  launch_pass<K, MODE_IOU>(1, w.rows, m, w.cols, n, device, s, ign_best, ign_thr_enc, w.col_best, w.row_e, 0.f, nullptr,
                               nullptr);
-  launch_pass<K, MODE_IOU, 2>(w.rows, m, w.cols, n, device, s, ign_best, ign_thr_enc, nullptr, w.row_e, p.min_pos,
+  launch_pass<K, MODE_IOU>(2, w.rows, m, w.cols, n, device, s, ign_best, ign_thr_enc, nullptr, w.row_e, p.min_pos,
                               w.col_last, w.row_first);
   (void)sizeof(P);
   return assign_tail(w, m, n, ign_best, ign_thr_enc, p, s);
@@ -315,12 +343,13 @@ int aidet_assign_wrt_overlaps_f32(const float* overlaps, int m, int n, long long
   cudaStream_t s = (cudaStream_t)stream;
   void* ws = (void*)align_up((size_t)(uintptr_t)workspace, 128);
   AssignWs w = assign_layout(ws, m, n, 0, 0);
-  if (int rc = assign_clear(w, m, n, 0, s)) return rc;
+  assign_init_kernel<<<ceil_div(m > n ? m : n, 256), 256, 0, s>>>(m, n, w);
+  count_launch(1);
   const int tile_rows = pick_tile_rows(m, n, device);
   dim3 grid(ceil_div(n, kACols), ceil_div(m, tile_rows));
-  assign_pass_kernel<HbbKind, MODE_IOU, 1, true><<<grid, kACols, 0, s>>>(nullptr, m, nullptr, n, overlaps, ld, tile_rows,
+  assign_pass_kernel<HbbKind, MODE_IOU, true><<<grid, kACols, 0, s>>>(nullptr, m, nullptr, n, overlaps, ld, tile_rows, 1,
                                                                           nullptr, 0, w.col_best, w.row_e, 0.f, nullptr, nullptr);
-  assign_pass_kernel<HbbKind, MODE_IOU, 2, true><<<grid, kACols, 0, s>>>(nullptr, m, nullptr, n, overlaps, ld, tile_rows,
+  assign_pass_kernel<HbbKind, MODE_IOU, true><<<grid, kACols, 0, s>>>(nullptr, m, nullptr, n, overlaps, ld, tile_rows, 2,
                                                                           nullptr, 0, nullptr, w.row_e, min_pos_iou,
                                                                           w.col_last, w.row_first);
   count_launch(2);

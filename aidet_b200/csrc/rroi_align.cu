@@ -416,45 +416,21 @@ rroi_align_fast_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __
 
 
 // ---------------------------------------------------------------------------------------
-// Forward with merged taps.  ncu on the kernel above (profiles/r1b): DRAM traffic equals the
-// algorithmic bytes but the L1 data pipe is 80-85 % busy -- every tap of every sample is a
-// 512-byte warp load (4 wavefronts) even when neighbouring samples of a bin hit the same
-// pixel.  At the FPN level a RoI is mapped to, a bin is 2-4 feature pixels and its 2x2 samples
-// are 1-2 px apart, so the 16 taps of a bin touch ~9 distinct pixels (57 % on config C3).
-// Here the taps of each bin are merged by pixel while the table is built -- one entry per
-// distinct pixel, weight = sum of the taps' weights in tap order (deterministic) -- and the
-// CTA's bins form ONE flat entry list that a lane walks with a ring of kRing loads in flight
-// (the ring spans bin boundaries).  Entry = (byte offset | flags, weight): bit 0 = last entry
-// of its bin (store + reset the accumulator), bit 1 = placeholder of a bin whose samples were
-// all rejected (nothing is loaded).  sample_num 1 and 2 (every AIDet config: 2).
-constexpr int kEntries = 256;        // entry-list capacity per CTA
-constexpr int kMergePasses = 4;
-      // bins are merged kMergePasses x (warps x 32 / T) at a time, in registers
-
-template <int G>
-__device__ __forceinline__ SampleTap make_sample_fixed(const RoiGeom& g, int bin, int smp, int pw) {
-  const int iy = smp / G, ix = smp - iy * G;                       // G x G sampling grid (compile time)
-  const int p_h = bin / pw, p_w = bin - p_h * pw;
-  float yy = g.yb + p_h * g.bin_h + (iy + .5f) * g.bin_h / (float)G;
-  float xx = g.xb + p_w * g.bin_w + (ix + .5f) * g.bin_w / (float)G;
-  float x = g.ox + xx * g.cs - yy * g.sn;
-  float y = g.oy + xx * g.sn + yy * g.cs;
-  SampleTap t;
-  if (y < -1.0f || y > (float)g.H || x < -1.0f || x > (float)g.W) {
-    t.off[0] = -1; t.off[1] = t.off[2] = t.off[3] = 0;
-    t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
-    return t;
-  }
-  if (y <= 0.f) y = 0.f;
-  if (x <= 0.f) x = 0.f;
-  int yl = (int)y, xl = (int)x, yh, xh;
-  if (yl >= g.H - 1) { yh = yl = g.H - 1; y = (float)yl; } else yh = yl + 1;
-  if (xl >= g.W - 1) { xh = xl = g.W - 1; x = (float)xl; } else xh = xl + 1;
-  float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
-  t.off[0] = yl * g.W + xl; t.off[1] = yl * g.W + xh; t.off[2] = yh * g.W + xl; t.off[3] = yh * g.W + xh;
-  t.w[0] = hy * hx; t.w[1] = hy * lx; t.w[2] = ly * hx; t.w[3] = ly * lx;
-  return t;
-}
+// Forward with merged taps ("tap list").  ncu on the kernel above: DRAM traffic equals the algorithmic bytes,
+// but every tap of every sample is a 512-byte warp load = 4 L1 wavefronts at ~2 cycles each
+// (B300_MICROARCH.md: 2.07 cyc/wavefront inside one LDG), i.e. ~64 B/clk/SM: 3.3 GB of tap loads on C3 take
+// 0.177 ms whatever DRAM does -- the kernel sits exactly on that L1 bound.  At the FPN level a RoI is mapped
+// to, a bin is 2-4 feature pixels and its 2x2 samples are 1-2 px apart, so the 16 taps of a bin touch ~9
+// distinct pixels (57 % on C3).  Here one CTA owns a whole RoI (<= kTLBins bins):
+//   build  : T = 4*G*G lanes per bin compute one tap each; taps of a bin that hit the same pixel are merged
+//            with __match_any_sync (weight = sum in tap order, deterministic) into a per-bin list of
+//            (byte offset, weight) entries in shared memory -- two barriers per CTA in all;
+//   consume: a warp owns one (bin, 32-channel-quad chunk) task at a time and walks the bin's list kChunk
+//            entries per step: two broadcast LDS.128 per four entries, predicated LDG.128s all issued before
+//            the FFMAs; consecutive warps take the chunks of the same bin, so both halves of a pixel's
+//            1 KB are fetched together.
+// sample_num 1 and 2 (every AIDet config: 2).
+constexpr int kTLBins = 64;          // bins per CTA
 
 // One tap (corner j of sample smp of `bin`) of a G x G sampling grid: pixel index in the plane (-1: rejected
 // sample) and weight -- the lane-per-tap form of make_sample_fixed.
@@ -484,21 +460,41 @@ __device__ __forceinline__ float group_sum_ordered(unsigned m, float w) {
   return ws;
 }
 
-// G = sample_num (1 or 2): T = 4*G*G taps per bin live in T consecutive lanes of a warp and are merged
-// with __match_any_sync / shuffles -- no shared-memory round trips, two barriers in all.
-template <int G, int RING>
-__global__ void __launch_bounds__(256)
-rroi_align_fwd_merged_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __restrict__ rois, int roi_fmt,
-                             const int* __restrict__ roi_level, int ph, int pw, int variant,
-                             float* __restrict__ out, int CL, int nslots, int groups_per_roi, int bins_per_group) {
+// NP pairs of tap-list entries (two per 16-byte shared-memory word): all loads first, then the FFMAs, no branches --
+// so the loads of a bin are in flight together (8 at a time: a warp keeps 4 KB in flight).
+template <int NP>
+__device__ __forceinline__ float4 taplist_consume(const uint4* __restrict__ e, const char* __restrict__ fc, float4 acc) {
+  constexpr int A = NP > 4 ? 4 : NP;
+  uint4 p[A];
+  float4 v[2 * A];
+#pragma unroll
+  for (int j = 0; j < A; ++j) p[j] = e[j];
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    v[2 * j] = __ldg(reinterpret_cast<const float4*>(fc + p[j].x));
+    v[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(fc + p[j].z));
+  }
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    acc = vfma(__uint_as_float(p[j].y), v[2 * j], acc);
+    acc = vfma(__uint_as_float(p[j].w), v[2 * j + 1], acc);
+  }
+  if constexpr (NP > 4) acc = taplist_consume<NP - 4>(e + 4, fc, acc);
+  return acc;
+}
+
+template <int G, int OCC>
+__global__ void __launch_bounds__(256, OCC)
+rroi_align_fwd_taplist_kernel(RoiLevels lv, int n_levels, int N, int C, const float* __restrict__ rois, int roi_fmt,
+                              const int* __restrict__ roi_level, int ph, int pw, int variant,
+                              float* __restrict__ out, int groups_per_roi, int bins_per_group, int chunk_shift) {
   constexpr int S = G * G, T = 4 * S, BPW = 32 / T;
-  __shared__ __align__(8) uint2 raw[kEntries];      // merged entries, T slots per bin
-  __shared__ __align__(8) uint2 ent[kEntries];      // the flat entry list
-  __shared__ int cnt[kEntries / T];                 // entries per bin (placeholder included)
+  __shared__ __align__(16) uint2 ent[kTLBins * T];     // per bin: T slots, the first cnt[b] hold merged entries
+  __shared__ int cnt[kTLBins];                         // entries per bin, padded to an even number
   const int k = blockIdx.x / groups_per_roi;
   const int grp = blockIdx.x - k * groups_per_roi;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  RoiGeom g;                                        // every thread decodes the RoI (uniform): no broadcast barrier
+  RoiGeom g;                                           // every thread decodes the RoI (uniform): no broadcast barrier
   {
     const float* r = rois + (size_t)k * roi_fmt;
     int lvl = roi_level ? __ldg(roi_level + k) : 0;
@@ -514,100 +510,60 @@ rroi_align_fwd_merged_kernel(RoiLevels lv, int n_levels, int N, int C, const flo
   const int bin_begin = grp * bins_per_group, bin_end = min(nbins, bin_begin + bins_per_group);
   const int nb = bin_end - bin_begin;
   const int nch = C >> 2;
-  const bool batch_ok = g.batch >= 0 && g.batch < N;
-  float4* outk = reinterpret_cast<float4*>(out) + (size_t)k * nbins * nch;
-  if (!batch_ok) {
+  float4* outk = reinterpret_cast<float4*>(out) + ((size_t)k * nbins + bin_begin) * nch;
+  if (!(g.batch >= 0 && g.batch < N)) {
     float* o = reinterpret_cast<float*>(outk);
-    for (int i = bin_begin * C + tid; i < bin_end * C; i += blockDim.x) o[i] = 0.f;
+    for (int i = tid; i < nb * C; i += blockDim.x) o[i] = 0.f;
     return;
   }
   const float inv_count = g.inv_count;
   const unsigned pix_bytes = (unsigned)C * 4u;
   const int seg = lane & ~(T - 1), i_tap = lane & (T - 1);
-#pragma unroll 1
-  for (int p = 0; p < kMergePasses; ++p) {
-    const int b = (p * nwarps + warp) * BPW + lane / T;             // bin of this lane, local to the CTA
-    if ((p * nwarps + warp) * BPW >= nb) break;                     // warp uniform
-    const bool valid = b < nb;                                      // (whole T-lane segments agree)
-    unsigned off = 0xffffffffu; float w = 0.f;
-    if (valid) {
-      const SampleTap t = make_sample_fixed<G>(g, bin_begin + b, i_tap >> 2, pw);
-      const int j = i_tap & 3;
-      if (t.off[0] >= 0) {
-        off = (unsigned)(j == 0 ? t.off[0] : j == 1 ? t.off[1] : j == 2 ? t.off[2] : t.off[3]) * pix_bytes;
-        w = (j == 0 ? t.w[0] : j == 1 ? t.w[1] : j == 2 ? t.w[2] : t.w[3]) * inv_count;
-      }
-    }
-    const bool tap_ok = off != 0xffffffffu;
+  for (int p = warp; p * BPW < nb; p += nwarps) {                    // ---- build
+    const int b = p * BPW + lane / T;                                // bin of this lane, local to the CTA
+    const bool valid = b < nb;                                       // (whole T-lane segments agree)
+    int pix = -1; float w = 0.f;
+    if (valid) pix = sample_tap_fixed<G>(g, bin_begin + b, i_tap >> 2, i_tap & 3, pw, w);
+    const bool tap_ok = pix >= 0;
     // equal keys <=> same pixel of the same bin; rejected / idle lanes get unique keys
-    const unsigned long long key = tap_ok ? (((unsigned long long)off << 8) | (unsigned)(lane / T))
-                                          : (0x8000000000000000ULL | (unsigned)lane);
+    const unsigned key = tap_ok ? (((unsigned)pix << 3) | (unsigned)(lane / T)) : (0x80000000u | (unsigned)lane);
     const unsigned m = __match_any_sync(0xffffffffu, key);
     const bool f = tap_ok && (lane == __ffs(m) - 1);
-    float ws = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < T; ++jj) {                                // duplicates summed in tap order
-      const float wj = __shfl_sync(0xffffffffu, w, seg + jj);
-      if ((m >> (seg + jj)) & 1u) ws += wj;
-    }
-    const unsigned fb = (__ballot_sync(0xffffffffu, f) >> seg) & ((1u << T) - 1u);
+    const float ws = group_sum_ordered(m, w) * inv_count;            // duplicates summed in tap order
+    const unsigned fb = (__ballot_sync(0xffffffffu, f) >> seg) & ((T == 32) ? 0xffffffffu : ((1u << T) - 1u));
     const int c = __popc(fb), within = __popc(fb & ((1u << i_tap) - 1u));
-    if (valid && i_tap == 0) {
-      cnt[b] = max(c, 1);
-      if (c == 0) raw[b * T] = make_uint2(3u, 0u);                  // all samples rejected: placeholder
+    if (valid && i_tap == 0) cnt[b] = (c + 1) & ~1;
+    if (f) {
+      const unsigned off = (unsigned)pix * pix_bytes;
+      ent[b * T + within] = make_uint2(off, __float_as_uint(ws));
+      // odd count: one zero-weight copy of the last entry (an L1 hit) so that the consumer needs no predicates
+      if (within == c - 1 && (c & 1)) ent[b * T + c] = make_uint2(off, 0u);
     }
-    if (f) raw[b * T + within] = make_uint2(off | ((within == c - 1) ? 1u : 0u), __float_as_uint(ws));
   }
   __syncthreads();
-  for (int t = tid; t < nb * T; t += blockDim.x) {                  // per-bin runs -> one flat list
-    const int b = t / T, i = t - b * T;
-    if (i >= cnt[b]) continue;
-    int pos = i;
-    for (int q = 0; q < b; ++q) pos += cnt[q];
-    ent[pos] = raw[t];
-  }
-  __syncthreads();
-  const int slot = tid / CL, cl = tid - slot * CL;
-  if (slot >= nslots) return;
-  // slot s owns the consecutive bins [b0, b1) of this CTA and therefore one contiguous run of entries
-  const int b0 = (int)((long long)slot * nb / nslots), b1 = (int)((long long)(slot + 1) * nb / nslots);
-  int e_begin = 0;
-  for (int q = 0; q < b0; ++q) e_begin += cnt[q];
-  int e_end = e_begin;
-  for (int q = b0; q < b1; ++q) e_end += cnt[q];
+  // ---- consume: warp -> fixed channel chunk, bins strided (nwarps and the chunk count are powers of two)
+  const int ch = warp & ((1 << chunk_shift) - 1), cc = ch * 32 + lane;
+  if (cc >= nch) return;
   const size_t plane = (size_t)g.batch * g.H * g.W * C;
-  const char* feat = reinterpret_cast<const char*>(lv.feat[g.level] + plane);
+  const char* fc = reinterpret_cast<const char*>(lv.feat[g.level] + plane) + (unsigned)cc * 16u;
+  float4* dst = outk + cc;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int cc = cl; cc < nch; cc += CL) {
-    const char* fc = feat + (unsigned)cc * 16u;
-    float4* dst = outk + (size_t)(bin_begin + b0) * nch + cc;
-    float4 v[RING];
-    uint2 en[RING];
-#pragma unroll
-    for (int i = 0; i < RING; ++i) {
-      v[i] = zero; en[i] = make_uint2(0u, 0u);
-      if (e_begin + i < e_end) {
-        en[i] = ent[e_begin + i];
-        if (!(en[i].x & 2u)) v[i] = __ldg(reinterpret_cast<const float4*>(fc + (en[i].x & ~15u)));
-      }
-    }
+  for (int b = warp >> chunk_shift; b < nb; b += nwarps >> chunk_shift) {
+    const int c = cnt[b];
+    const uint4* e = reinterpret_cast<const uint4*>(ent + b * T);     // two entries per 16 bytes
     float4 acc = zero;
-    for (int base = e_begin; base < e_end; base += RING) {
-#pragma unroll
-      for (int i = 0; i < RING; ++i) {
-        const int e = base + i;
-        if (e < e_end) {                                              // uniform over the slot
-          acc = vfma(__uint_as_float(en[i].y), v[i], acc);
-          const bool last = en[i].x & 1u;
-          if (e + RING < e_end) {
-            en[i] = ent[e + RING];
-            if (en[i].x & 2u) v[i] = zero;
-            else v[i] = __ldg(reinterpret_cast<const float4*>(fc + (en[i].x & ~15u)));
-          }
-          if (last) { __stcs(dst, acc); dst += nch; acc = zero; }
-        }
-      }
+    switch (c >> 1) {                                     // warp-uniform; every case is branch-free straight-line code
+      case 1: acc = taplist_consume<1>(e, fc, acc); break;
+      case 2: acc = taplist_consume<2>(e, fc, acc); break;
+      case 3: acc = taplist_consume<3>(e, fc, acc); break;
+      case 4: acc = taplist_consume<4>(e, fc, acc); break;
+      case 5: acc = taplist_consume<5>(e, fc, acc); break;
+      case 6: acc = taplist_consume<6>(e, fc, acc); break;
+      case 7: acc = taplist_consume<7>(e, fc, acc); break;
+      case 8: acc = taplist_consume<8>(e, fc, acc); break;
+      default: break;                                     // c == 0: every sample of the bin was rejected
     }
+    __stcs(dst + (size_t)b * nch, acc);
   }
 }
 
@@ -868,15 +824,18 @@ static int check_common(const int* H, const int* W, const float* scale, int n_le
   return AIDET_OK;
 }
 
-// Experimental switch (AIDET_ROI_FWD_MERGED=1): forward with per-bin merged taps.  Measured on C3 (r1b): L1
-// wavefronts 222k -> 122k per SM as intended, but 2.2x the warp instructions (merge prologue per bin row +
-// 35 SASS instructions per entry) -> 0.307 ms vs 0.186 ms for the one-load-per-tap kernel, so it is off.
-static const bool g_roi_fwd_unmerged = [] { const char* e = getenv("AIDET_ROI_FWD_MERGED"); return !(e && e[0] == '1'); }();
+// Forward default = the tap-list kernel (merged taps).  History on C3: one load per tap 0.176 ms (on the L1 wavefront
+// bound); first merged version (r1b) 0.307 ms (merge prologue per bin row + 35 SASS instructions per entry); tap list
+// with branch-free per-count consumers 0.154 ms: 61.7 M warp instructions instead of 105.7 M, 57.6 M L1 sectors
+// instead of 98.2 M, now limited by load latency / DRAM efficiency of scattered 1 KB reads (profiles/r1e).
+// tuning / test switch (AIDET_ROI_FWD_UNMERGED=1): the per-sample forward (rroi_align_fast_kernel) instead of the tap-list kernel
+static const bool g_roi_fwd_unmerged = [] { const char* e = getenv("AIDET_ROI_FWD_UNMERGED"); return e && e[0] == '1'; }();
 
 // test switch (AIDET_ROI_BWD_UNMERGED=1): one tap per sample corner, no per-bin merge
 static const bool g_roi_bwd_unmerged = [] { const char* e = getenv("AIDET_ROI_BWD_UNMERGED"); return e && e[0] == '1'; }();
 static const int g_gather_px = [] { const char* e = getenv("AIDET_ROI_GATHER_PX"); int v = e ? atoi(e) : 8; return (v == 4 || v == 16) ? v : 8; }();   // pixels per gather warp (tuning)
-static const int g_fwd_ring = [] { const char* e = getenv("AIDET_ROI_FWD_RING"); return e ? atoi(e) : 4; }();   // loads in flight per lane (tuning)
+
+static const int g_tl_occ = [] { const char* e = getenv("AIDET_ROI_TL_OCC"); return e ? atoi(e) : 5; }();   // resident CTAs per SM the tap-list forward is compiled for (tuning)
 
 static int lanes_for(int nch) { int cl = 1; while (cl < nch && cl < 256) cl <<= 1; return cl; }
 
@@ -890,20 +849,21 @@ static int launch(RoiLevels& lv, int n_levels, int N, int C, const float* rois, 
   long long max_plane = 0;
   for (int l = 0; l < n_levels; l++) max_plane = max(max_plane, (long long)lv.H[l] * lv.W[l]);
   const bool fast = vec4 && sample_num > 0 && sample_num * sample_num <= kTable && max_plane * C * 4 < 0xffffffffLL;
-  if (fast && !BWD && sample_num <= 2 && !g_roi_fwd_unmerged) {
-    const int nch = C / 4;
-    const int CL = lanes_for(nch);
-    const int threads = max(CL, 32);
-    const int nslots = threads / CL;
-    const int T = 4 * sample_num * sample_num;
-    const int bins_per_group = min(pw, min(kEntries / T, kMergePasses * (threads / 32) * (32 / T)));
-    const int groups_per_roi = ceil_div(ph * pw, bins_per_group);
-#define AIDET_LAUNCH_MERGED(G_, R_)                                                                             \
-  rroi_align_fwd_merged_kernel<G_, R_><<<K * groups_per_roi, threads, 0, s>>>(                                  \
-      lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, pw, variant, io, CL, nslots, groups_per_roi, bins_per_group)
-    if (sample_num == 2) { if (g_fwd_ring == 8) AIDET_LAUNCH_MERGED(2, 8); else AIDET_LAUNCH_MERGED(2, 4); }
-    else                 { if (g_fwd_ring == 8) AIDET_LAUNCH_MERGED(1, 8); else AIDET_LAUNCH_MERGED(1, 4); }
-#undef AIDET_LAUNCH_MERGED
+  if (fast && !BWD && sample_num <= 2 && !g_roi_fwd_unmerged && max_plane < (1LL << 28) && C <= 1024) {
+    const int nbins = ph * pw;
+    const int groups_per_roi = ceil_div(nbins, kTLBins);
+    const int bins_per_group = ceil_div(nbins, groups_per_roi);
+    int chunk_shift = 0;                                  // 2^chunk_shift warps share a bin: 32 channel quads each
+    while ((32 << chunk_shift) < C / 4) ++chunk_shift;    // C <= 1024 -> <= 8 chunks = the CTA's 8 warps
+#define AIDET_LAUNCH_TAPLIST(G_, O_)                                                                           \
+  rroi_align_fwd_taplist_kernel<G_, O_><<<K * groups_per_roi, 256, 0, s>>>(lv, n_levels, N, C, rois, roi_fmt, roi_level, ph, \
+                                                                          pw, variant, io, groups_per_roi, bins_per_group, chunk_shift)
+    if (sample_num == 2) {
+      if (g_tl_occ == 4) AIDET_LAUNCH_TAPLIST(2, 4); else if (g_tl_occ == 6) AIDET_LAUNCH_TAPLIST(2, 6); else AIDET_LAUNCH_TAPLIST(2, 5);
+    } else {
+      AIDET_LAUNCH_TAPLIST(1, 5);
+    }
+#undef AIDET_LAUNCH_TAPLIST
   } else if (fast) {
     // The kernel is latency bound (ncu: no memory pipe above 65 %), so the grid is made of many small
     // CTAs -- one bin row of one RoI, channel lanes only -- that come and go independently: a CTA slot

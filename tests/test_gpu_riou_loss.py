@@ -25,7 +25,7 @@ def test_gradient_vs_finite_differences(cuda, mode):
     err = np.abs(g - fd)[smooth]
     assert err.max() < 2e-5, err.max()
     # forward of the gradient kernel == the aligned kernel
-    assert torch.equal(ov, F.riou_aligned(pred.to(cuda), target.to(cuda), mode))
+    assert float((ov - F.riou_aligned(pred.to(cuda), target.to(cuda), mode)).abs().max()) <= 1e-6
 
 
 def test_loss_backward_and_reductions(cuda):
@@ -51,7 +51,7 @@ def test_loss_backward_and_reductions(cuda):
     l2 = riou_loss(p2, far, reduction='sum')
     l2.backward()
     assert torch.isfinite(l2) and float(p2.grad.abs().max()) == 0.0
-    assert abs(float(l2) / 3000 + np.log(1e-6)) < 1e-4
+    assert abs(float(l2.detach()) / 3000 + np.log(1e-6)) < 1e-4
 
     m = RotatedIoULoss(loss_weight=2.0)
     base = riou_loss(p.detach(), t, reduction='none')
@@ -71,18 +71,15 @@ def test_target_gradient_and_descent(cuda):
     iou0.sum().backward()
     assert p.grad is not None and t.grad is not None
     assert float((p.grad[:, :2] + t.grad[:, :2]).abs().max()) < 1e-4          # translation invariance
+    # gradient ASCENT on the IoU with steps scaled to the box (d iou / d px ~ 1 / size): the mean IoU must rise
     x = pred.to(cuda).clone().requires_grad_(True)
-    opt = torch.optim.SGD([x], lr=1.0)
-    first = None
-    for _ in range(60):
-        opt.zero_grad()
-        iou = rotated_iou(x, target.to(cuda))
-        loss = (1 - iou).sum()
-        if first is None:
-            first = float(iou.mean())
-        loss.backward()
-        with torch.no_grad():                 # normalise the step per parameter scale (px vs rad)
-            x.grad[:, :4] *= 50.0
-            x.grad[:, 4] *= 0.05
-        opt.step()
-    assert float(rotated_iou(x, target.to(cuda)).mean()) > first + 0.15
+    tt = target.to(cuda)
+    first = float(rotated_iou(x, tt).mean())
+    for _ in range(40):
+        x.grad = None
+        rotated_iou(x, tt).sum().backward()
+        with torch.no_grad():
+            s2 = (x[:, 2] * x[:, 3]).unsqueeze(1)
+            x[:, :4] += 0.05 * s2 * x.grad[:, :4]
+            x[:, 4] += 0.05 * x.grad[:, 4]
+    assert float(rotated_iou(x, tt).mean()) > first + 0.25
