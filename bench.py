@@ -625,7 +625,7 @@ def run_ours(args, D):
                             "peak": hbm_peak, "unit": "GB/s",
                             "frac": (bytes_fwd + bytes_bwd) / ((fms + bms) * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": hbm_src,
-                            "traffic": ((TRAFFIC["rroi_align_fast_kernel_fwd"]["bytes"] + TRAFFIC["rroi_gather_kernel_bwd"]["bytes"])
+                            "traffic": ((TRAFFIC["rroi_align_fwd_taplist_kernel"]["bytes"] + TRAFFIC["rroi_gather_kernel_bwd"]["bytes"])
                                         if "rroi_gather_kernel_bwd" in TRAFFIC else None),
                             "traffic_source": "ncu dram read+write of the fwd kernel + the gather-backward kernel, one C3 launch each (%s)" % TRAFFIC.get("source"),
                             "fwd_frac": bytes_fwd / (fms * 1e-3) / 1e9 / hbm_peak,

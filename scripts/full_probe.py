@@ -1,5 +1,6 @@
 """One launch of every hot kernel at its bench size, for `ncu --set full` captures:
-riou 32768^2 dense, batched NMS (C2 and one dense 16384-box group), RoIAlign C3 fwd + gather bwd."""
+riou 32768^2 dense, batched NMS (C2 and one dense 16384-box group), RoIAlign C3 fwd + gather bwd, the fused max-IoU
+assignment (anchor grid of a 1024 tile x 128 truths) and the rotated-IoU-loss gradient kernel (65536 pairs)."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -26,4 +27,9 @@ o = F.rroi_align_forward(feats, rois, scales, (7, 7), 2, 2, lvl)
 go = torch.randn_like(o)
 grads = [torch.empty_like(f) for f in feats]
 F.rroi_align_backward_gather(go, grads, rois, scales, 2, 2, lvl)
+from aidet_b200.core import MaxIoUAssigner
+_, gt, _, lab = synth.assign_case(1024, 128, seed=21)
+MaxIoUAssigner(0.7, 0.3, 0.3, True).assign(synth.anchor_grid().to(dev), gt.to(dev), None, lab.to(dev))
+pr, tg = synth.regression_pairs(65536, seed=22)
+F.riou_aligned_grad(pr.to(dev), tg.to(dev))
 torch.cuda.synchronize()
