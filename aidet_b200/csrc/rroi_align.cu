@@ -548,6 +548,8 @@ rroi_align_fwd_taplist_kernel(RoiLevels lv, int n_levels, int N, int C, const fl
   const char* fc = reinterpret_cast<const char*>(lv.feat[g.level] + plane) + (unsigned)cc * 16u;
   float4* dst = outk + cc;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // (An L2 prefetch of the warp's next bin was measured and is slower: 0.165 vs 0.154 ms -- the extra requests compete
+  //  with the demand loads.)
   for (int b = warp >> chunk_shift; b < nb; b += nwarps >> chunk_shift) {
     const int c = cnt[b];
     const uint4* e = reinterpret_cast<const uint4*>(ent + b * T);     // two entries per 16 bytes
