@@ -132,3 +132,17 @@ def test_analytic_riou_gradient_special_cases(sim_grad):
     assert np.abs(g[1] - want).max() < 1e-6
     want[2] = -want[2]                                   # negative w: |w| is used, the gradient flips sign
     assert np.abs(g[2] - want).max() < 1e-6
+
+
+def test_delta2bbox_reference_doctest():
+    # mmdet/core/bbox/transforms.py:57-71
+    from aidet_b200.core import bbox2delta, delta2bbox
+    rois = torch.Tensor([[0., 0., 1., 1.], [0., 0., 1., 1.], [0., 0., 1., 1.], [5., 5., 5., 5.]])
+    deltas = torch.Tensor([[0., 0., 0., 0.], [1., 1., 1., 1.], [0., 0., 2., -1.], [0.7, -1.9, -0.5, 0.3]])
+    want = torch.Tensor([[0.0000, 0.0000, 1.0000, 1.0000], [0.2817, 0.2817, 4.7183, 4.7183],
+                         [0.0000, 0.6321, 7.3891, 0.3679], [5.8967, 2.9251, 5.5033, 3.2749]])
+    assert (delta2bbox(rois, deltas, max_shape=(32, 32)) - want).abs().max() < 1e-4
+    per_img = delta2bbox(rois.view(2, 2, 4), deltas.view(2, 2, 4), max_shape=(torch.tensor([[32.], [4.]]), torch.tensor([[32.], [4.]])))
+    assert (per_img[0] - want[:2]).abs().max() < 1e-4 and float(per_img[1].max()) <= 3.0
+    p, g = torch.tensor([[1., 2., 25., 28.]]), torch.tensor([[3., 4., 20., 30.]])
+    assert (delta2bbox(p, bbox2delta(p, g)) - g).abs().max() < 1e-4
