@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaidet_b200.so")
+LIB_PATH = os.environ.get("AIDET_B200_LIB") or os.path.join(_HERE, "libaidet_b200.so")   # override: kernel-tuning builds
 
 MODE_IOU, MODE_IOF = 0, 1
 CMP_GT, CMP_GE = 0, 1

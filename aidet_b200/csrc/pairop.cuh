@@ -41,6 +41,11 @@ template <class K>
 struct PairOp {
   using S = typename K::Row;   // staged (matrix row)
   using R = typename K::Col;   // registers (matrix col)
+  // bounding circles meet (the early-out test of overlap())
+  __device__ static __forceinline__ bool near(const S& s, const R& r) {
+    float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
+    return !(fmaf(dx, dx, dy * dy) > rr * rr);
+  }
   __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) {
     float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
     if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;

@@ -258,8 +258,13 @@ struct NmsTile { int start, ng, r0, cq0, nr, g; };   // nr == 0: no tile left
 // Tiles are handed out by a ticket counter (balanced although diagonal tiles are cheaper and groups differ in
 // size).  Thread 0 is the scheduler: while the CTA works on tile k it draws the ticket of tile k+1, skips tiles
 // left of the diagonal, and starts the TMA copy of its row records into the other staging buffer.
+// 4 resident CTAs per SM (<= 64 registers).  A dual-row step like the overlap-matrix kernel's was measured here and
+// is slower (one dense 16384-box group: mask 0.780 vs 0.763 ms): the ballot per row already breaks the chains.
+#ifndef AIDET_NMS_MINB
+#define AIDET_NMS_MINB 4
+#endif
 template <class O, bool GE>
-__global__ void __launch_bounds__(kTileCols)
+__global__ void __launch_bounds__(kTileCols, AIDET_NMS_MINB)
 nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
                 const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
                 int n_groups, const float* __restrict__ thr, int n_thr, float one, int tile_rows,

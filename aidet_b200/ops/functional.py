@@ -219,11 +219,13 @@ def _scalar_thr(value, device):
     return t
 
 
-def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False):
+def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False, sync=True):
     """Batched greedy NMS.  boxes (n,4|5|8), scores (n,), group_ids (n,) int or None.
 
     iou_thr: float, or a (n_groups,) tensor / sequence of per-group thresholds.
-    Returns keep (k,) int64, ascending original index.
+    Returns keep (k,) int64, ascending original index.  sync=False: no host read-back -- returns (keep (n,) whose first
+    n_keep entries are valid, n_keep (1,) int32 device tensor); the call is then capturable in a CUDA graph (pass
+    n_groups and a float / tensor threshold so that nothing else touches the host).
     """
     fmt = boxes.size(-1)
     boxes = _f32c(boxes, fmt, "boxes")
@@ -234,7 +236,8 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
         raise ValueError("scores must have one entry per box")
     device = boxes.device
     if n == 0:
-        return torch.zeros((0,), dtype=torch.long, device=device)
+        empty = torch.zeros((0,), dtype=torch.long, device=device)
+        return empty if sync else (empty, torch.zeros((1,), dtype=torch.int32, device=device))
     if group_ids is None:
         n_groups = 1
         gids = None
@@ -267,6 +270,8 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
                                           thr.numel(), n_groups, L.CMP_GE if cmp_ge else L.CMP_GT,
                                           int(bool(plus_one)), L.dptr(keep), L.dptr(n_keep), C.c_void_p(aligned),
                                           ws_bytes, dev, L.stream_ptr(dev)), "aidet_nms_batched_f32")
+    if not sync:
+        return keep, n_keep
     k = int(n_keep.item())
     return keep[:k]
 

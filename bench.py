@@ -739,6 +739,62 @@ def run_ours(args, D):
                              "workload": "riou_loss forward + backward on 65536 aligned theta-OBB pairs (aligned overlap "
                                          "kernel + analytic-gradient kernel + the -log/clamp/sum torch ops around them)"}
 
+
+    # ---------------- latency of the small configs: C1 and C2, eager and under CUDA-graph replay
+    if args.workload in ("all", "nms", "iou"):
+        from aidet_b200.core import rbbox_overlaps as _rov
+
+        def graph_us(fn, iters=200):
+            """fn() must not touch the host.  -> (eager us per call, graph-replay us per call), device time."""
+            L.prof_enable(False)                          # no event records inside a capture
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            eager = e0.elapsed_time(e1) / iters * 1e3
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            gr.replay()
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(iters):
+                gr.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            L.prof_enable(True)
+            return eager, e0.elapsed_time(e1) / iters * 1e3
+
+        a1, s1 = synth.dota_boxes(2000, side=1024, seed=0)
+        b1, _ = synth.dota_boxes(2000, side=1024, seed=1)
+        a1, s1, b1 = a1.to(dev), s1.to(dev), b1.to(dev)
+        c1_out = torch.empty((2000, 2000), device=dev)
+
+        def c1_step():
+            Fn.riou_matrix(a1, b1, out=c1_out)
+            Fn.nms_batched(a1, s1, None, 0.1, n_groups=1, sync=False)
+
+        cb2, cs2, cg2, ng2 = nms_inputs(dense=False, images=1)
+        cb2, cs2, cg2 = cb2.to(dev), cs2.to(dev), cg2.to(dev)
+
+        def c2_step():
+            Fn.nms_batched(cb2, cs2, cg2, 0.5, n_groups=ng2, sync=False)
+
+        c1_e, c1_g = graph_us(c1_step)
+        c2_e, c2_g = graph_us(c2_step)
+        line["latency"] = {
+            "c1": {"eager_us": c1_e, "graph_us": c1_g,
+                   "workload": "C1: rotated IoU matrix 2000x2000 theta-OBB + single-class rotated NMS @0.1 of the 2000 boxes "
+                               "(6 kernels), no host read-back; back-to-back calls, L2 warm"},
+            "c2": {"eager_us": c2_e, "graph_us": c2_g, "boxes": int(cb2.shape[0]),
+                   "workload": "C2: batched rotated NMS of the 15 classes (3 kernels), keep count left on the device"},
+            "how": "CUDA events around 200 back-to-back calls; graph = one torch.cuda.CUDAGraph replayed 200 times"}
+
     line["clocks"] = sampler.stop() if sampler else None
     line["ffma_peak_tflops_measured"] = ffma
     return line, dev

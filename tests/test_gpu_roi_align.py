@@ -209,3 +209,25 @@ def test_gather_backward_edge_cases(cuda):
         ok = rois[:, 0] < 2
         gref = O.roi_align_bwd(go[ok].contiguous().numpy(), (2, 12, 12, c), rois[ok].numpy(), 0.25, 2, O.ROI_V2_ALIGNED)
         _close(gf[0].cpu().numpy(), gref, "gather edge C=%d" % c)
+
+
+@pytest.mark.parametrize("c,out,sample_num", [(256, 7, 2), (192, 14, 2), (512, 7, 1), (40, 14, 1), (1024, 3, 2), (1280, 3, 2),
+                                              (64, 9, 2)])
+def test_taplist_forward_shapes(cuda, c, out, sample_num):
+    """The tap-list forward over its whole shape range: 1-8 channel chunks per bin (C = 40 ... 1024; 1280 falls back to
+    the per-sample kernel), one and several CTAs per RoI (7x7 = 49 bins, 14x14 = 196 bins), sample_num 1 and 2, RoIs
+    hanging over the border, fully outside, and with a batch index out of range (-> zeros)."""
+    g = torch.Generator().manual_seed(c + out)
+    n, hw, scale = 2, 40, 0.25
+    feat = torch.randn(n, hw, hw, c, generator=g)                       # NHWC
+    rois, _ = synth.rotated_rois(24, n, tile=int(hw / scale), seed=c)
+    rois[:, 3:5] = rois[:, 3:5].clamp(max=120)
+    extra = torch.tensor([[0, -6.0, 80.0, 40.0, 30.0, 0.5], [1, 400.0, 400.0, 20.0, 20.0, 0.2], [7, 50.0, 50.0, 30.0, 30.0, 0.1],
+                          [1, 159.5, 159.5, 6.0, 2.0, -0.9], [0, 80.0, 80.0, 1.0, 1.0, 0.0]])
+    rois = torch.cat([rois, extra])
+    for variant in (O.ROI_V1, O.ROI_V2_ALIGNED):
+        y = F.rroi_align_forward([feat.to(cuda)], rois.to(cuda), [scale], (out, out), sample_num, variant)
+        ok = rois[:, 0] < n
+        ref = O.roi_align_fwd(feat.numpy(), rois[ok].numpy(), scale, (out, out), sample_num, variant)
+        _close(y[ok.to(cuda)].cpu().numpy(), ref, "taplist C=%d out=%d sn=%d v=%d" % (c, out, sample_num, variant))
+        assert float(y[~ok.to(cuda)].abs().max()) == 0.0
