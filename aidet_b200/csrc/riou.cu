@@ -120,25 +120,31 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
 #if AIDET_RIOU_DUAL
     if constexpr (!std::is_same<K, HbbKind>::value) {
       // two rows per step: when both rows have a lane whose bounding circles meet (the dense case), the two clippings
-      // run as ONE straight-line block, so the scheduler can interleave two independent dependency chains; the
-      // skip granularity stays (row, warp) exactly as with the per-lane early-out.
+      // run as ONE straight-line block, so the scheduler can interleave two independent dependency chains.
+      // Probe: do the first two rows of the tile both have a lane whose bounding circles meet this warp's columns?
+      // Dense tiles then take the dual-row loop, sparse tiles the plain per-lane early-out loop below (both give
+      // identical values; the probe only picks the faster schedule).
+      bool dual = false;
+      if (nr >= 2) dual = __any_sync(0xffffffffu, P::near(st[0], me)) && __any_sync(0xffffffffu, P::near(st[1], me));
+      if (dual) {
 #pragma unroll 1
-      for (; r + 2 <= nr; r += 2) {
-        const S sa = st[r], sb = st[r + 1];
-        const bool ha = P::near(sa, me), hb = P::near(sb, me);
-        const bool wa = __any_sync(0xffffffffu, ha), wb = __any_sync(0xffffffffu, hb);
-        float va = 0.0f, vb = 0.0f;
-        if (wa && wb) {
-          const float ia = K::inter(sa, me), ib = K::inter(sb, me);
-          va = ha ? finish_overlap(ia, sa.area, me.area, MODE) : 0.0f;
-          vb = hb ? finish_overlap(ib, sb.area, me.area, MODE) : 0.0f;
-        } else if (wa) {
-          va = ha ? finish_overlap(K::inter(sa, me), sa.area, me.area, MODE) : 0.0f;
-        } else if (wb) {
-          vb = hb ? finish_overlap(K::inter(sb, me), sb.area, me.area, MODE) : 0.0f;
+        for (; r + 2 <= nr; r += 2) {
+          const S sa = st[r], sb = st[r + 1];
+          const bool ha = P::near(sa, me), hb = P::near(sb, me);
+          const bool wa = __any_sync(0xffffffffu, ha), wb = __any_sync(0xffffffffu, hb);
+          float va = 0.0f, vb = 0.0f;
+          if (wa && wb) {
+            const float ia = K::inter(sa, me), ib = K::inter(sb, me);
+            va = ha ? finish_overlap(ia, sa.area, me.area, MODE) : 0.0f;
+            vb = hb ? finish_overlap(ib, sb.area, me.area, MODE) : 0.0f;
+          } else if (wa) {
+            va = ha ? finish_overlap(K::inter(sa, me), sa.area, me.area, MODE) : 0.0f;
+          } else if (wb) {
+            vb = hb ? finish_overlap(K::inter(sb, me), sb.area, me.area, MODE) : 0.0f;
+          }
+          put(va);
+          put(vb);
         }
-        put(va);
-        put(vb);
       }
     }
 #endif
