@@ -51,6 +51,8 @@ def parse():
     p.add_argument("--iou-n", type=int, default=100000, help="IoU matrix side (config C4: 100000)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    p.add_argument("--quick", action="store_true", help="profiler runs: 5 graph replays instead of 200, no per-(image, level) "
+                                                        "comparison loop in the RPN leg (thousands of launches under ncu)")
     return p.parse_args()
 
 
@@ -602,11 +604,13 @@ def run_ours(args, D):
         L.prof_read(L.PROF_NMS_MASK, reset=True)
         rms, rl = timed(D, dev, args.steps, args.warmup, rpn_select, flush=flush)
         rk_ms, rk_cnt = L.prof_read(L.PROF_NMS_MASK, reset=True)
-        lms, _ = timed(D, dev, max(2, args.steps // 3), 1, rpn_loop, flush=flush)
+        lms = float('nan')
+        if not args.quick:
+            lms, _ = timed(D, dev, max(2, args.steps // 3), 1, rpn_loop, flush=flush)
         r_pairs = group_pairs(r_gids.cpu(), r_ng)
         nms["rpn"] = {"value": r_props.shape[0] * G / (rms / args.steps) / 1e3, "unit": "Mboxes/s", "ms_per_step": rms / args.steps,
                       "boxes": int(r_props.shape[0]), "groups": r_ng, "gpu_launches": int(rl),
-                      "per_level_loop_ms": lms / max(2, args.steps // 3),
+                      "per_level_loop_ms": None if args.quick else lms / max(2, args.steps // 3),
                       "mask_kernel_ms": rk_ms / max(rk_cnt, 1),
                       "workload": "RPN proposal selection (rpn_head.py:94-108) for 8 images x 5 FPN levels of a 1024 tile: HBB NMS "
                                   "@0.7 (+1) of the top-2000 per (image, level) in ONE batched launch, [:nms_post], per-image top-2000; "
@@ -744,7 +748,7 @@ def run_ours(args, D):
     if args.workload in ("all", "nms", "iou"):
         from aidet_b200.core import rbbox_overlaps as _rov
 
-        def graph_us(fn, iters=200):
+        def graph_us(fn, iters=(5 if args.quick else 200)):
             """fn() must not touch the host.  -> (eager us per call, graph-replay us per call), device time."""
             L.prof_enable(False)                          # no event records inside a capture
             for _ in range(3):
