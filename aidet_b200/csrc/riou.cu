@@ -15,8 +15,10 @@
 //               t+1 overlaps the arithmetic of tile t.  Row records are read from
 //               shared memory with warp-uniform 128-bit loads (broadcast); the result
 //               row segment of a warp is one 128 B coalesced streaming store.
-//   bound     : FP32 issue (about 170 instructions per pair, no tensor-core shape);
-//               output traffic 4 B/pair is ~1/6 of HBM peak at full ALU rate.
+//               Per tile a two-row probe picks a dual-row loop (dense tiles: two clippings per
+//               step as one straight-line block) or the per-lane early-out loop (sparse tiles).
+//   bound     : FP32 issue (157 instructions per pair, 85 % of the issue slots; no tensor-core
+//               shape); output traffic 4 B/pair is ~1/8 of HBM peak at the achieved rate.
 #include <type_traits>
 
 #include "common.cuh"

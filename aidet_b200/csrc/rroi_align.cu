@@ -8,13 +8,16 @@
 // element and every thread recomputes the sample geometry.  Here:
 //   - features are channels-last (N,H,W,C): a bilinear tap is a contiguous C*4-byte run,
 //     read with 128-bit loads by consecutive lanes (lanes = channel quads)
-//   - one CTA per RoI; the sample geometry (4 tap offsets + 4 weights per sample point,
-//     border rules of roi_align_kernel.cu:17-62) is computed ONCE per RoI into shared
-//     memory and broadcast to the channel lanes
+//   - one CTA per RoI; the sample geometry (tap offsets + weights per sample point, border
+//     rules of roi_align_kernel.cu:17-62) is computed ONCE per RoI into shared memory and
+//     broadcast to the channel lanes; the default forward (sample_num 1/2) merges the taps
+//     of a bin by pixel first (tap list, see rroi_align_fwd_taplist_kernel)
 //   - all FPN levels run in one launch (per-RoI level id), rotated and axis-aligned RoIs
 //     share the kernel (theta = 0 reproduces v1/v2)
-//   - backward scatters with 128-bit vector reductions (red.global.add.v4.f32)
-// Bound: HBM/L2 bandwidth (no reuse of arithmetic; ~2 flop per byte read).
+//   - backward: gather form (taps bucketed per pixel, every gradient pixel written once, no
+//     atomics on the maps) for fixed sampling grids; scatter form with 128-bit vector
+//     reductions (red.global.add.v4.f32) for adaptive grids
+// Bound: HBM bandwidth (~2 flop per byte read); the forward additionally by load latency.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 

@@ -43,6 +43,20 @@ def test_library_loads_and_reports_errors_without_gpu():
     assert rc == -1 and b"n_thr" in lib.aidet_last_error()
     rc = lib.aidet_rroi_align_fwd_f32(None, None, None, None, 9, 1, 1, None, 5, None, 0, 7, 7, 2, 0, None, 0, None)
     assert rc == -1 and b"n_levels" in lib.aidet_last_error()
+    rc = lib.aidet_max_iou_assign_f32(None, 0, None, 4, 5, None, 0, 0.0, 0, 0.5, 0.0, 0.5, 0.0, 1, None, None, None, None,
+                                      None, 0, 0, None)
+    assert rc == -1 and b"at least one gt" in lib.aidet_last_error()
+    rc = lib.aidet_max_iou_assign_f32(None, 3, None, 4, 6, None, 0, 0.0, 0, 0.5, 0.0, 0.5, 0.0, 1, None, None, None, None,
+                                      None, 0, 0, None)
+    assert rc == -1 and b"fmt" in lib.aidet_last_error()
+    rc = lib.aidet_assign_wrt_overlaps_f32(None, 3, 4, 2, 0.5, 0.0, 0.5, 0.0, 1, None, None, None, None, None, 0, 0, None)
+    assert rc == -1 and b"null pointer" in lib.aidet_last_error()
+    rc = lib.aidet_riou_aligned_grad_f32(None, None, 4, 8, 0, None, None, None, None, 0, None)
+    assert rc == -1 and b"theta-OBB" in lib.aidet_last_error()
+    # workspace sizes grow with every operand and cover the records (32 B per theta-OBB)
+    w0 = lib.aidet_assign_workspace_bytes(100, 2000, 0, 5)
+    assert w0 >= (100 + 2000) * 32 + 2000 * 16 and lib.aidet_assign_workspace_bytes(100, 2000, 7, 5) > w0
+    assert lib.aidet_assign_workspace_bytes(100, 2000, 0, 0) < w0          # matrix form: no records
     assert lib.aidet_launch_count() == 0
 
 
@@ -64,6 +78,17 @@ def test_python_surface_matches_reference_names():
     assert list(inspect.signature(core.rbbox_overlaps).parameters) == ["rbboxes1", "rbboxes2", "mode", "is_aligned"]
     assert list(inspect.signature(core.multiclass_thetaobb_nms).parameters)[:5] == [
         "multi_rbboxes", "multi_scores", "score_thr", "polygon_nms_iou_thr", "max_num"]
+    # max_iou_assigner.py:37-44, iou_loss.py:131, rpn_head.py:55-62, transforms.py:34-39
+    assert list(inspect.signature(core.MaxIoUAssigner.__init__).parameters) == [
+        "self", "pos_iou_thr", "neg_iou_thr", "min_pos_iou", "gt_max_assign_all", "ignore_iof_thr", "ignore_wrt_candidates",
+        "gpu_assign_thr"]
+    assert list(inspect.signature(core.MaxIoUAssigner.assign).parameters) == [
+        "self", "bboxes", "gt_bboxes", "gt_bboxes_ignore", "gt_labels"]
+    from aidet_b200 import models
+    assert list(inspect.signature(models.RotatedIoULoss.__init__).parameters) == ["self", "eps", "reduction", "loss_weight"]
+    assert list(inspect.signature(models.rpn_get_bboxes_single).parameters)[:7] == [
+        "cls_scores", "bbox_preds", "mlvl_anchors", "img_shape", "scale_factor", "cfg", "rescale"]
+    assert list(inspect.signature(core.delta2bbox).parameters) == ["rois", "deltas", "means", "stds", "max_shape", "wh_ratio_clip"]
 
 
 def test_no_cpu_fallback():

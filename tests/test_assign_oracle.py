@@ -146,3 +146,37 @@ def test_delta2bbox_reference_doctest():
     assert (per_img[0] - want[:2]).abs().max() < 1e-4 and float(per_img[1].max()) <= 3.0
     p, g = torch.tensor([[1., 2., 25., 28.]]), torch.tensor([[3., 4., 20., 30.]])
     assert (delta2bbox(p, bbox2delta(p, g)) - g).abs().max() < 1e-4
+
+
+def test_rpn_decode_stage_on_cpu():
+    """Stage 1 of the RPN proposal path (top-k, delta2bbox with per-image bounds, size filter) is plain tensor code:
+    checked on the CPU against rpn_head.py:64-92 restated per image and per level."""
+    from aidet_b200.core import delta2bbox
+    from aidet_b200.models.anchor_heads.rpn_head import decode_levels
+    g = torch.Generator().manual_seed(4)
+    n_img, sizes, cfg = 2, (16, 8, 4), dict(nms_pre=200, min_bbox_size=4)
+    cls = [torch.randn(n_img, 3, s, s, generator=g) for s in sizes]
+    reg = [torch.randn(n_img, 12, s, s, generator=g) * 0.3 for s in sizes]
+    anc = []
+    for s in sizes:
+        st = 64 // s
+        ys, xs = torch.meshgrid(torch.arange(s, dtype=torch.float32), torch.arange(s, dtype=torch.float32), indexing='ij')
+        c = torch.stack([xs, ys], -1).reshape(-1, 1, 2) * st + (st - 1) / 2
+        half = torch.tensor([[8.0, 4.0], [6.0, 6.0], [4.0, 8.0]]) * st / 4
+        anc.append(torch.cat([c - half, c + half], -1).reshape(-1, 4))
+    shapes = [(64, 64, 3), (50, 60, 3)]
+    props, gids = decode_levels(cls, reg, anc, shapes, cfg)
+    for i in range(n_img):
+        for lvl in range(len(sizes)):
+            scores = cls[lvl][i].permute(1, 2, 0).reshape(-1).sigmoid()
+            d = reg[lvl][i].permute(1, 2, 0).reshape(-1, 4)
+            a = anc[lvl]
+            if scores.shape[0] > cfg['nms_pre']:
+                _, topk = scores.topk(cfg['nms_pre'])
+                d, a, scores = d[topk], a[topk], scores[topk]
+            p = delta2bbox(a, d, (0, 0, 0, 0), (1, 1, 1, 1), shapes[i])
+            ok = (p[:, 2] - p[:, 0] + 1 >= 4) & (p[:, 3] - p[:, 1] + 1 >= 4)
+            want = torch.cat([p[ok], scores[ok].unsqueeze(-1)], -1)
+            got = props[gids == lvl * n_img + i]
+            assert got.shape == want.shape and torch.allclose(got, want, atol=1e-5)
+    assert bool((gids[1:] >= gids[:-1]).all())          # blocks in ascending (level, image) order
