@@ -349,6 +349,90 @@ AIDET_HD void quad_prepare(const float* box8, QuadRow* row, QuadCol* col) {
   }
 }
 
+// ------------------------------------- d(overlap)/d(corner coordinates), point-OBB (convex quads)
+//
+// Same transport-theorem form as rect_inter_grad: moving corner a_k moves its two edges; a point at fraction t of
+// edge (a_k -> a_k+1) moves with (1 - t) da_k + t da_k+1, the outward normal times the edge length is (d.y, -d.x), so
+//     dI/da_k   += (d.y, -d.x) * [ (t1 - t0) - (t1^2 - t0^2) / 2 ]        [t0, t1] = part of the edge inside B
+//     dI/da_k+1 += (d.y, -d.x) *   (t1^2 - t0^2) / 2
+// The interval comes from the four half-planes of B (CCW, convex) -- min/max closed forms again.
+
+// x, y: CCW corners of A; bx, by: CCW corners of convex B.  g[2k], g[2k+1] = d area(A ^ B) / d (x_k, y_k).
+AIDET_HD void quad_inter_grad(const float* x, const float* y, const float* bx, const float* by, float* g) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) g[k] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int q = (k + 1) & 3;
+    const float dx = x[q] - x[k], dy = y[q] - y[k];
+    float lo = 0.0f, hi = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int jq = (j + 1) & 3;
+      const float ex = bx[jq] - bx[j], ey = by[jq] - by[j];
+      const float f0 = ex * (y[k] - by[j]) - ey * (x[k] - bx[j]);        // cross(e, a_k - b_j): >= 0 inside
+      const float f1 = ex * dy - ey * dx;                                 // its slope along the edge
+      const float tc = -f0 * frcp(f1 + copysignf(1e-30f, f1));
+      // f1 > 0: inside for t >= tc;  f1 < 0: inside for t <= tc;  f1 ~ 0: the whole edge is in or out with f0
+      const bool flat = fabsf(f1) <= 1e-12f * (fabsf(ex) + fabsf(ey)) * (fabsf(dx) + fabsf(dy));
+      if (flat) { if (f0 < 0.0f) hi = -1.0f; }
+      else if (f1 > 0.0f) lo = fmaxf(lo, tc);
+      else hi = fminf(hi, tc);
+    }
+    hi = fmaxf(hi, lo);
+    const float len = hi - lo, half2 = 0.5f * len * (hi + lo);          // (t1^2 - t0^2) / 2, exactly 0 for an empty interval
+    const float wk = len - half2, wq = half2;
+    g[2 * k] += dy * wk;     g[2 * k + 1] -= dx * wk;
+    g[2 * q] += dy * wq;     g[2 * q + 1] -= dx * wq;
+  }
+}
+
+// Overlap of two convex quads (x1,y1,...,x4,y4, either orientation) and its gradient w.r.t. all 16 coordinates.
+AIDET_HD float quad_overlap_grad(const float* a8, const float* b8, int mode, float* ga, float* gb) {
+  QuadRow ra; QuadCol cb; QuadRow rb;
+  quad_prepare(a8, &ra, (QuadCol*)nullptr);
+  quad_prepare(b8, &rb, &cb);
+#pragma unroll
+  for (int k = 0; k < 8; k++) { ga[k] = 0.0f; gb[k] = 0.0f; }
+  float ddx = ra.mx - rb.mx, ddy = ra.my - rb.my, rr = ra.rad + rb.rad;
+  if (fmaf(ddx, ddx, ddy * ddy) > rr * rr) return 0.0f;
+  float inter = quad_inter(ra, cb);
+  inter = fminf(fmaxf(inter, 0.0f), fminf(ra.area, rb.area));
+  // CCW corners about a common origin (the centroid of A keeps the products small)
+  float ax[4], ay[4], bxx[4], byy[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    ax[k] = ra.x[k]; ay[k] = ra.y[k];
+    bxx[k] = rb.x[k] + (rb.mx - ra.mx); byy[k] = rb.y[k] + (rb.my - ra.my);
+  }
+  float ia[8], ib[8];
+  quad_inter_grad(ax, ay, bxx, byy, ia);
+  quad_inter_grad(bxx, byy, ax, ay, ib);
+  const float S = ra.area + rb.area;
+  const float den = (mode == MODE_IOF) ? ra.area : (mode == MODE_IOF_B) ? rb.area : (S - inter);
+  if (!(den > 0.0f)) return 0.0f;
+  const float rden = 1.0f / den, r2 = rden * rden;
+  const float P = (mode == MODE_IOU) ? S : den;
+  const float qa = (mode == MODE_IOF_B) ? 0.0f : inter, qb = (mode == MODE_IOF) ? 0.0f : inter;
+  // quad_prepare made both quads CCW by swapping corners 1 and 3 when needed: undo that for the caller's order
+  const float sa = (a8[2] - a8[0]) * (a8[5] - a8[1]) - (a8[3] - a8[1]) * (a8[4] - a8[0])
+                 + (a8[4] - a8[0]) * (a8[7] - a8[1]) - (a8[5] - a8[1]) * (a8[6] - a8[0]);
+  const float sb = (b8[2] - b8[0]) * (b8[5] - b8[1]) - (b8[3] - b8[1]) * (b8[4] - b8[0])
+                 + (b8[4] - b8[0]) * (b8[7] - b8[1]) - (b8[5] - b8[1]) * (b8[6] - b8[0]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int kp = (k + 1) & 3, km = (k + 3) & 3;
+    // d area / d corner k of a CCW polygon: ( (y_k+1 - y_k-1) / 2, (x_k-1 - x_k+1) / 2 )
+    const float dAax = 0.5f * (ay[kp] - ay[km]), dAay = 0.5f * (ax[km] - ax[kp]);
+    const float dAbx = 0.5f * (byy[kp] - byy[km]), dAby = 0.5f * (bxx[km] - bxx[kp]);
+    const int ka = (sa < 0.0f && (k & 1)) ? (k ^ 2) : k;      // 1 <-> 3
+    const int kb = (sb < 0.0f && (k & 1)) ? (k ^ 2) : k;
+    ga[2 * ka] = (ia[2 * k] * P - qa * dAax) * r2;  ga[2 * ka + 1] = (ia[2 * k + 1] * P - qa * dAay) * r2;
+    gb[2 * kb] = (ib[2 * k] * P - qb * dAbx) * r2;  gb[2 * kb + 1] = (ib[2 * k + 1] * P - qb * dAby) * r2;
+  }
+  return inter * rden;
+}
+
 // ------------------------------------------------------------- HBB (+1)
 
 // mmdet/ops/nms/src/nms_kernel.cu:14-22 (devIoU) / nms_cpu.cpp:47-55

@@ -170,25 +170,27 @@ __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restri
   out[i] = PairOp<K>::overlap(r, c, mode);
 }
 
-// d overlap(a[i], b[i]) / d (cx,cy,w,h,theta) of both boxes, scaled by the upstream gradient (theta-OBB only):
-// the backward of the aligned overlap, i.e. of the rotated IoU loss (rotated counterpart of
-// mmdet/models/losses/iou_loss.py:10-27).  One thread per pair; geom.cuh: rect_overlap_grad.
+// d overlap(a[i], b[i]) / d (box parameters) of both boxes, scaled by the upstream gradient: the backward of the aligned
+// overlap, i.e. of the rotated IoU loss (rotated counterpart of mmdet/models/losses/iou_loss.py:10-27).  FMT 5:
+// (cx,cy,w,h,theta), geom.cuh: rect_overlap_grad; FMT 8: the corner coordinates of convex quads, quad_overlap_grad.
+// One thread per pair.
+template <int FMT>
 __global__ void __launch_bounds__(256) riou_aligned_grad_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                 int n, int mode, const float* __restrict__ grad_ov,
                                                                 float* __restrict__ ov, float* __restrict__ grad_a,
                                                                 float* __restrict__ grad_b) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float pa[5], pb[5], ga[5], gb[5];
+  float pa[FMT], pb[FMT], ga[FMT], gb[FMT];
 #pragma unroll
-  for (int k = 0; k < 5; k++) { pa[k] = a[(size_t)i * 5 + k]; pb[k] = b[(size_t)i * 5 + k]; }
-  float v = rect_overlap_grad(pa, pb, mode, ga, gb);
-  float go = grad_ov ? grad_ov[i] : 1.0f;
+  for (int k = 0; k < FMT; k++) { pa[k] = a[(size_t)i * FMT + k]; pb[k] = b[(size_t)i * FMT + k]; }
+  const float v = (FMT == 5) ? rect_overlap_grad(pa, pb, mode, ga, gb) : quad_overlap_grad(pa, pb, mode, ga, gb);
+  const float go = grad_ov ? grad_ov[i] : 1.0f;
   if (ov) ov[i] = v;
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
-    if (grad_a) grad_a[(size_t)i * 5 + k] = go * ga[k];
-    if (grad_b) grad_b[(size_t)i * 5 + k] = go * gb[k];
+  for (int k = 0; k < FMT; k++) {
+    if (grad_a) grad_a[(size_t)i * FMT + k] = go * ga[k];
+    if (grad_b) grad_b[(size_t)i * FMT + k] = go * gb[k];
   }
 }
 
@@ -327,14 +329,15 @@ int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int m
 
 int aidet_riou_aligned_grad_f32(const float* a, const float* b, int n, int fmt, int mode, const float* grad_ov,
                                 float* ov, float* grad_a, float* grad_b, int device, void* stream) {
-  AIDET_REQUIRE(fmt == 5, "aidet_riou_aligned_grad_f32: only theta-OBB (fmt 5) has a gradient, got fmt %d", fmt);
+  AIDET_REQUIRE(fmt == 5 || fmt == 8, "aidet_riou_aligned_grad_f32: fmt must be 5 (theta-OBB) or 8 (convex point-OBB), got %d", fmt);
   AIDET_REQUIRE(mode == AIDET_MODE_IOU || mode == AIDET_MODE_IOF, "aidet_riou_aligned_grad_f32: bad mode %d", mode);
   AIDET_REQUIRE(n >= 0, "aidet_riou_aligned_grad_f32: negative size");
   if (n == 0) return AIDET_OK;
   AIDET_REQUIRE(a && b, "aidet_riou_aligned_grad_f32: null pointer");
   if (int rc = set_device(device)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  riou_aligned_grad_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, grad_ov, ov, grad_a, grad_b);
+  if (fmt == 5) riou_aligned_grad_kernel<5><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, grad_ov, ov, grad_a, grad_b);
+  else riou_aligned_grad_kernel<8><<<ceil_div(n, 256), 256, 0, s>>>(a, b, n, mode, grad_ov, ov, grad_a, grad_b);
   count_launch(1);
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;

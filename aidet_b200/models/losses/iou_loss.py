@@ -23,8 +23,8 @@ class _RotatedIoU(Function):
     def forward(ctx, pred, target, mode):
         if not pred.is_cuda:
             raise NotImplementedError('rotated_iou has no CPU implementation')
-        assert pred.shape == target.shape and pred.dim() == 2 and pred.size(1) == 5, \
-            'rotated_iou takes aligned (n, 5) <cx, cy, w, h, theta> boxes'
+        assert pred.shape == target.shape and pred.dim() == 2 and pred.size(1) in (5, 8), \
+            'rotated_iou takes aligned (n, 5) <cx, cy, w, h, theta> or (n, 8) <x1, y1, ..., x4, y4> boxes'
         ctx.mode = mode
         ctx.save_for_backward(pred, target)
         return F.riou_aligned(pred, target, mode).to(pred.dtype)
@@ -39,7 +39,8 @@ class _RotatedIoU(Function):
 
 
 def rotated_iou(pred, target, mode='iou'):
-    """Differentiable aligned overlap of theta-OBBs: pred, target (n, 5) <cx, cy, w, h, theta[rad]> -> (n,)."""
+    """Differentiable aligned overlap of oriented boxes: pred, target (n, 5) <cx, cy, w, h, theta[rad]> or (n, 8) convex
+    <x1, y1, ..., x4, y4> -> (n,)."""
     if pred.size(0) == 0:
         return pred.new_zeros((0, ))
     return _RotatedIoU.apply(pred, target, mode)
@@ -73,13 +74,13 @@ def _weighted(loss_func):
 
 @_weighted
 def riou_loss(pred, target, eps=1e-6):
-    """-log(rotated IoU) of aligned theta-OBBs, pred / target (n, 5) (iou_loss.py:10-27 for oriented boxes)."""
+    """-log(rotated IoU) of aligned oriented boxes, pred / target (n, 5) or (n, 8) (iou_loss.py:10-27 for OBBs)."""
     ious = rotated_iou(pred, target).clamp(min=eps)
     return -ious.log()
 
 
 class RotatedIoULoss(nn.Module):
-    """`IoULoss` (iou_loss.py:129-165) on <cx, cy, w, h, theta> boxes: same arguments, same reduction rules."""
+    """`IoULoss` (iou_loss.py:129-165) on <cx, cy, w, h, theta> or 8-point boxes: same arguments, same reduction rules."""
 
     def __init__(self, eps=1e-6, reduction='mean', loss_weight=1.0):
         super(RotatedIoULoss, self).__init__()

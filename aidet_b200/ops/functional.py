@@ -103,16 +103,19 @@ def riou_aligned(a, b, mode="iou"):
 
 
 def riou_aligned_grad(a, b, grad_ov=None, mode="iou", want_b=True):
-    """Backward of `riou_aligned` for theta-OBB pairs: (ov (n,), grad_a (n,5), grad_b (n,5) | None), the gradients
-    scaled by `grad_ov` (n,) when given.  aidet_riou_aligned_grad_f32."""
+    """Backward of `riou_aligned` for theta-OBB (n,5) or convex point-OBB (n,8) pairs: (ov (n,), grad_a (n,fmt),
+    grad_b (n,fmt) | None), the gradients scaled by `grad_ov` (n,) when given.  aidet_riou_aligned_grad_f32."""
     assert mode in ("iou", "iof")
-    a, b = _f32c(a, 5, "a"), _f32c(b, 5, "b")
+    fmt = a.size(-1)
+    if fmt not in (5, 8):
+        raise ValueError("riou_aligned_grad takes (n, 5) or (n, 8) boxes, got %s" % (tuple(a.shape),))
+    a, b = _f32c(a, fmt, "a"), _f32c(b, fmt, "b")
     if a.shape != b.shape:
         raise ValueError("aligned overlaps need equal shapes, got %s and %s" % (tuple(a.shape), tuple(b.shape)))
     n = a.size(0)
     ov = torch.empty((n,), dtype=torch.float32, device=a.device)
-    ga = torch.empty((n, 5), dtype=torch.float32, device=a.device)
-    gb = torch.empty((n, 5), dtype=torch.float32, device=a.device) if want_b else None
+    ga = torch.empty((n, fmt), dtype=torch.float32, device=a.device)
+    gb = torch.empty((n, fmt), dtype=torch.float32, device=a.device) if want_b else None
     if n == 0:
         return ov, ga, gb
     if grad_ov is not None:
@@ -121,7 +124,7 @@ def riou_aligned_grad(a, b, grad_ov=None, mode="iou", want_b=True):
         assert grad_ov.numel() == n
     dev = a.device.index
     with torch.cuda.device(dev):
-        L.check(L.lib().aidet_riou_aligned_grad_f32(L.dptr(a), L.dptr(b), n, 5,
+        L.check(L.lib().aidet_riou_aligned_grad_f32(L.dptr(a), L.dptr(b), n, fmt,
                                                     L.MODE_IOF if mode == "iof" else L.MODE_IOU, L.dptr(grad_ov),
                                                     L.dptr(ov), L.dptr(ga), L.dptr(gb), dev, L.stream_ptr(dev)),
                 "aidet_riou_aligned_grad_f32")

@@ -83,10 +83,11 @@ int aidet_riou_matrix_mcast_f32(const float* a, int m, const float* b, int n, in
 int aidet_riou_aligned_f32(const float* a, const float* b, int n, int fmt, int mode, float* out,
                            int device, void* stream);
 
-/* Backward of the aligned overlap for theta-OBB pairs (fmt must be 5): grad_a[i] = grad_ov[i] * d ovr(a[i], b[i]) /
- * d (cx,cy,w,h,theta of a[i]), likewise grad_b; grad_ov NULL = ones; ov (n), grad_a (n,5), grad_b (n,5) may each be
- * NULL.  This is what makes the rotated IoU loss trainable -- the rotated counterpart of iou_loss
- * (mmdet/models/losses/iou_loss.py:10-27), which gets its gradient from autograd through bbox_overlaps. */
+/* Backward of the aligned overlap: grad_a[i] = grad_ov[i] * d ovr(a[i], b[i]) / d (parameters of a[i]), likewise grad_b.
+ * fmt 5: (cx,cy,w,h,theta); fmt 8: the corner coordinates of CONVEX quads (either orientation).  grad_ov NULL = ones;
+ * ov (n), grad_a (n,fmt), grad_b (n,fmt) may each be NULL.  This is what makes the rotated IoU loss trainable -- the
+ * rotated counterpart of iou_loss (mmdet/models/losses/iou_loss.py:10-27), which gets its gradient from autograd
+ * through bbox_overlaps. */
 int aidet_riou_aligned_grad_f32(const float* a, const float* b, int n, int fmt, int mode, const float* grad_ov,
                                 float* ov, float* grad_a, float* grad_b, int device, void* stream);
 

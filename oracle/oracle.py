@@ -82,14 +82,17 @@ def riou_aligned(a, b, mode="iou", algo=ALGO_SH):
 
 
 def riou_aligned_grad_fd(a, b, mode="iou", step=1e-6):
-    """theta-OBB pairs in float64 -> (overlap (n,), central-difference gradient (n,10) w.r.t. a's then b's
-    (cx,cy,w,h,theta)).  The checker for the analytic gradient of the rotated IoU loss."""
-    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, 5))
-    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1, 5))
+    """theta-OBB (n,5) or point-OBB (n,8) pairs in float64 -> (overlap (n,), central-difference gradient (n, 2*fmt)
+    w.r.t. a's then b's parameters).  The checker for the analytic gradient of the rotated IoU loss."""
+    fmt = np.asarray(a).shape[-1]
+    assert fmt in (5, 8)
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, fmt))
+    b = np.ascontiguousarray(np.asarray(b, dtype=np.float64).reshape(-1, fmt))
     assert a.shape == b.shape
     ov = np.empty((a.shape[0],), np.float64)
-    grad = np.empty((a.shape[0], 10), np.float64)
-    lib().oracle_riou_aligned_grad_fd(_p(a), _p(b), C.c_int(a.shape[0]), C.c_int({"iou": 0, "iof": 1, "iof_b": 2}[mode]),
+    grad = np.empty((a.shape[0], 2 * fmt), np.float64)
+    fn = lib().oracle_riou_aligned_grad_fd if fmt == 5 else lib().oracle_riou_aligned_grad_fd8
+    fn(_p(a), _p(b), C.c_int(a.shape[0]), C.c_int({"iou": 0, "iof": 1, "iof_b": 2}[mode]),
                                       C.c_double(step), _p(ov), _p(grad))
     return ov, grad
 

@@ -225,6 +225,31 @@ void oracle_riou_aligned_grad_fd(const double* a, const double* b, int n, int mo
   }
 }
 
+/* the same for point-OBBs with DOUBLE corner coordinates: grad (n,16) */
+static double riou_pair_d8(const double* a, const double* b, int mode) {
+  pt qa[4], qb[4];
+  for (int i = 0; i < 4; i++) { qa[i].x = a[2 * i]; qa[i].y = a[2 * i + 1]; qb[i].x = b[2 * i]; qb[i].y = b[2 * i + 1]; }
+  if (mode == 2) return pair_overlap(qb, qa, 1, 0);
+  return pair_overlap(qa, qb, mode, 0);
+}
+
+void oracle_riou_aligned_grad_fd8(const double* a, const double* b, int n, int mode, double step, double* ov,
+                                  double* grad) {
+#pragma omp parallel for
+  for (int i = 0; i < n; i++) {
+    double p[16];
+    for (int k = 0; k < 8; k++) { p[k] = a[8 * (size_t)i + k]; p[8 + k] = b[8 * (size_t)i + k]; }
+    ov[i] = riou_pair_d8(p, p + 8, mode);
+    for (int k = 0; k < 16; k++) {
+      double keep = p[k];
+      p[k] = keep + step; double fp = riou_pair_d8(p, p + 8, mode);
+      p[k] = keep - step; double fm = riou_pair_d8(p, p + 8, mode);
+      p[k] = keep;
+      grad[16 * (size_t)i + k] = (fp - fm) / (2 * step);
+    }
+  }
+}
+
 void oracle_riou_matrix(const float* a, int m, const float* b, int n, int fmt, int mode, int algo,
                         double* out) {
   pt* qb = (pt*)malloc(sizeof(pt) * 4 * (size_t)(n > 0 ? n : 1));

@@ -33,3 +33,9 @@ extern "C" void sim_riou_aligned_grad(const float* a, const float* b, int n, int
   for (int i = 0; i < n; i++)
     out[i] = rect_overlap_grad(a + 5 * (size_t)i, b + 5 * (size_t)i, mode, grad + 10 * (size_t)i, grad + 10 * (size_t)i + 5);
 }
+
+// point-OBB form: a, b (n,8); grad (n,16) = d ov / d (a corners, b corners)
+extern "C" void sim_riou_aligned_grad8(const float* a, const float* b, int n, int mode, float* out, float* grad) {
+  for (int i = 0; i < n; i++)
+    out[i] = quad_overlap_grad(a + 8 * (size_t)i, b + 8 * (size_t)i, mode, grad + 16 * (size_t)i, grad + 16 * (size_t)i + 8);
+}

@@ -51,8 +51,8 @@ def test_library_loads_and_reports_errors_without_gpu():
     assert rc == -1 and b"fmt" in lib.aidet_last_error()
     rc = lib.aidet_assign_wrt_overlaps_f32(None, 3, 4, 2, 0.5, 0.0, 0.5, 0.0, 1, None, None, None, None, None, 0, 0, None)
     assert rc == -1 and b"null pointer" in lib.aidet_last_error()
-    rc = lib.aidet_riou_aligned_grad_f32(None, None, 4, 8, 0, None, None, None, None, 0, None)
-    assert rc == -1 and b"theta-OBB" in lib.aidet_last_error()
+    rc = lib.aidet_riou_aligned_grad_f32(None, None, 4, 4, 0, None, None, None, None, 0, None)
+    assert rc == -1 and b"fmt must be 5" in lib.aidet_last_error()
     # workspace sizes grow with every operand and cover the records (32 B per theta-OBB)
     w0 = lib.aidet_assign_workspace_bytes(100, 2000, 0, 5)
     assert w0 >= (100 + 2000) * 32 + 2000 * 16 and lib.aidet_assign_workspace_bytes(100, 2000, 7, 5) > w0

@@ -96,8 +96,10 @@ def sim_grad():
         b = np.ascontiguousarray(b, np.float32)
         out = np.empty((len(a),), np.float32)
         g = np.empty((len(a), 10), np.float32)
-        lib.sim_riou_aligned_grad(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), len(a), mode,
-                                  out.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p))
+        fn = lib.sim_riou_aligned_grad if a.shape[1] == 5 else lib.sim_riou_aligned_grad8
+        g = np.empty((len(a), 2 * a.shape[1]), np.float32)
+        fn(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), len(a), mode, out.ctypes.data_as(C.c_void_p),
+           g.ctypes.data_as(C.c_void_p))
         return out.astype(np.float64), g.astype(np.float64)
     return run
 
@@ -180,3 +182,26 @@ def test_rpn_decode_stage_on_cpu():
             got = props[gids == lvl * n_img + i]
             assert got.shape == want.shape and torch.allclose(got, want, atol=1e-5)
     assert bool((gids[1:] >= gids[:-1]).all())          # blocks in ascending (level, image) order
+
+
+@pytest.mark.parametrize("mode,mi", [("iou", 0), ("iof", 1)])
+@pytest.mark.parametrize("noise", [0.0, 0.04])
+def test_point_obb_gradient_matches_finite_differences(sim_grad, mode, mi, noise):
+    """csrc/geom.cuh: quad_overlap_grad (gradient w.r.t. the 2 x 8 corner coordinates of convex quads, FP32) vs central
+    differences of the float64 oracle; rectangles and perturbed (general convex) quads, both orientations."""
+    pred, target = synth.regression_pairs(3000, seed=5)
+    a8, b8 = synth.thetaobb2pointobb(pred).numpy(), synth.thetaobb2pointobb(target).numpy()
+    rng = np.random.default_rng(2)
+    size = np.sqrt(pred[:, 2] * pred[:, 3]).numpy()[:, None]
+    a8 = (a8 + rng.normal(0, noise, a8.shape) * size).astype(np.float32)
+    b8 = (b8 + rng.normal(0, noise, b8.shape) * size).astype(np.float32)
+    a8[::2] = a8[::2].reshape(-1, 4, 2)[:, ::-1].reshape(-1, 8)          # clockwise corner order for half of them
+    b8[::3] = b8[::3].reshape(-1, 4, 2)[:, ::-1].reshape(-1, 8)
+    ov, g = sim_grad(a8, b8, mi)
+    ref, fd = O.riou_aligned_grad_fd(a8, b8, mode, 1e-5)
+    _, fd2 = O.riou_aligned_grad_fd(a8, b8, mode, 2e-5)
+    smooth = np.abs(fd - fd2).max(1) < 1e-6
+    assert smooth.mean() > 0.99 and np.abs(ov - ref).max() < 1e-5 and (ref > 0.05).mean() > 0.9
+    assert np.abs(g - fd)[smooth].max() < 2e-5
+    # translating both quads together changes nothing: the 16 x- (y-) derivatives sum to 0
+    assert np.abs(g[:, 0::2].sum(1)).max() < 1e-5 and np.abs(g[:, 1::2].sum(1)).max() < 1e-5

@@ -83,3 +83,30 @@ def test_target_gradient_and_descent(cuda):
             x[:, :4] += 0.05 * s2 * x.grad[:, :4]
             x[:, 4] += 0.05 * x.grad[:, 4]
     assert float(rotated_iou(x, tt).mean()) > first + 0.25
+
+
+@pytest.mark.parametrize("mode", ["iou", "iof"])
+def test_point_obb_gradient_and_loss(cuda, mode):
+    """fmt 8: gradient w.r.t. the corner coordinates of convex quads vs central differences of the float64 oracle,
+    and the loss on (n, 8) boxes through autograd."""
+    pred, target = synth.regression_pairs(8000, seed=15)
+    a8, b8 = synth.thetaobb2pointobb(pred), synth.thetaobb2pointobb(target)
+    g = torch.Generator().manual_seed(3)
+    size = torch.sqrt(pred[:, 2] * pred[:, 3])[:, None]
+    a8 = (a8 + torch.randn(a8.shape, generator=g) * 0.03 * size).contiguous()
+    b8 = (b8 + torch.randn(b8.shape, generator=g) * 0.03 * size).contiguous()
+    a8[::2] = a8[::2].reshape(-1, 4, 2).flip(1).reshape(-1, 8)
+    ov, ga, gb = F.riou_aligned_grad(a8.to(cuda), b8.to(cuda), None, mode)
+    ref, fd = O.riou_aligned_grad_fd(a8.numpy(), b8.numpy(), mode, 1e-5)
+    _, fd2 = O.riou_aligned_grad_fd(a8.numpy(), b8.numpy(), mode, 2e-5)
+    smooth = np.abs(fd - fd2).max(1) < 1e-6
+    assert smooth.mean() > 0.99 and np.abs(ov.cpu().numpy() - ref).max() <= 1e-5
+    got = torch.cat([ga, gb], 1).cpu().numpy().astype(np.float64)
+    assert np.abs(got - fd)[smooth].max() < 2e-5
+    if mode == "iou":
+        p = a8.to(cuda).requires_grad_(True)
+        loss = riou_loss(p, b8.to(cuda), reduction='sum')
+        loss.backward()
+        want = -fd[:, :8] / np.maximum(ref, 1e-6)[:, None]
+        ok = smooth & (ref > 1e-3)
+        assert np.abs(p.grad.cpu().numpy() - want)[ok].max() < 1e-3 * max(1.0, np.abs(want[ok]).max())
