@@ -58,3 +58,24 @@ def delta2bbox(rois, deltas, means=(0, 0, 0, 0), stds=(1, 1, 1, 1), max_shape=No
             x1, x2 = x1.clamp(min=0, max=wmax), x2.clamp(min=0, max=wmax)
             y1, y2 = y1.clamp(min=0, max=hmax), y2.clamp(min=0, max=hmax)
     return torch.stack([x1, y1, x2, y2], dim=-1)
+
+
+def bbox_flip(bboxes, img_shape):
+    """Flip boxes horizontally (mmdet/core/bbox/transforms.py:113-131, tensor branch): bboxes (n, 4k), img_shape (h, w, ..)."""
+    assert bboxes.shape[-1] % 4 == 0
+    flipped = bboxes.clone()
+    flipped[:, 0::4] = img_shape[1] - bboxes[:, 2::4] - 1
+    flipped[:, 2::4] = img_shape[1] - bboxes[:, 0::4] - 1
+    return flipped
+
+
+def bbox_mapping(bboxes, img_shape, scale_factor, flip):
+    """Original image scale -> testing scale (transforms.py:134-139)."""
+    new_bboxes = bboxes * scale_factor
+    return bbox_flip(new_bboxes, img_shape) if flip else new_bboxes
+
+
+def bbox_mapping_back(bboxes, img_shape, scale_factor, flip):
+    """Testing scale -> original image scale (transforms.py:142-146)."""
+    new_bboxes = bbox_flip(bboxes, img_shape) if flip else bboxes
+    return new_bboxes / scale_factor

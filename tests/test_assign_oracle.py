@@ -205,3 +205,17 @@ def test_point_obb_gradient_matches_finite_differences(sim_grad, mode, mi, noise
     assert np.abs(g - fd)[smooth].max() < 2e-5
     # translating both quads together changes nothing: the 16 x- (y-) derivatives sum to 0
     assert np.abs(g[:, 0::2].sum(1)).max() < 1e-5 and np.abs(g[:, 1::2].sum(1)).max() < 1e-5
+
+
+def test_bbox_mapping_and_aug_merging_on_cpu():
+    """transforms.py:113-146 and merge_augs.py:46-78 (pure tensor code)."""
+    from aidet_b200.core import bbox_flip, bbox_mapping, bbox_mapping_back, merge_aug_bboxes, merge_aug_scores
+    b = torch.tensor([[10., 5., 30., 25., 0., 1., 2., 3.]])
+    f = bbox_flip(b, (100, 200, 3))
+    assert f.tolist() == [[169., 5., 189., 25., 197., 1., 199., 3.]]
+    m = bbox_mapping(b, (100, 200, 3), 2.0, True)
+    assert torch.allclose(bbox_mapping_back(m, (100, 200, 3), 2.0, True), b)
+    metas = [[dict(img_shape=(100, 200, 3), scale_factor=1.0, flip=False)], [dict(img_shape=(100, 200, 3), scale_factor=2.0, flip=True)]]
+    bb, sc = merge_aug_bboxes([b, m], [torch.ones(1, 2), torch.zeros(1, 2)], metas, None)
+    assert torch.allclose(bb, b) and sc.tolist() == [[0.5, 0.5]]
+    assert merge_aug_scores([torch.ones(2), torch.zeros(2)]).tolist() == [0.5, 0.5]

@@ -130,3 +130,28 @@ def test_public_entry_points(cuda):
         assert torch.equal(canon(one.cpu()), canon(both[i].cpu()))
     with pytest.raises(NotImplementedError):
         rpn_get_bboxes(cls, reg, anc, metas, CFG)
+
+
+def test_merge_aug_proposals(cuda):
+    """merge_augs.py:8-43: proposals of two augmented views (one flipped and scaled) mapped back, one NMS, top-k."""
+    from aidet_b200.core import bbox_mapping, merge_aug_proposals
+    g = torch.Generator().manual_seed(6)
+    xy = torch.rand(300, 2, generator=g) * 150
+    wh = torch.rand(300, 2, generator=g) * 60 + 8
+    base = torch.cat([xy, xy + wh, torch.rand(300, 1, generator=g)], 1)
+    view2 = base.clone()
+    view2[:, :4] = bbox_mapping(base[:, :4] + torch.randn(300, 4, generator=g), (240, 260, 3), 1.5, True)
+    view2[:, 4] = torch.rand(300, generator=g)
+    metas = [dict(img_shape=(240, 260, 3), scale_factor=1.0, flip=False), dict(img_shape=(240, 260, 3), scale_factor=1.5, flip=True)]
+    cfg = dict(nms_thr=0.7, max_num=100)
+    got = merge_aug_proposals([base.to(cuda), view2.to(cuda)], metas, cfg).cpu()
+    # restated on the CPU with the oracle NMS (`>`: CUDA tensors take the CUDA comparison, nms_kernel.cu:61)
+    from aidet_b200.core import bbox_mapping_back
+    rec = view2.clone()
+    rec[:, :4] = bbox_mapping_back(view2[:, :4], (240, 260, 3), 1.5, True)
+    allp = torch.cat([base, rec], 0)
+    keep, _ = O.nms(allp[:, :4].numpy(), allp[:, 4].numpy(), 0.7, cmp_ge=False, plus_one=True)
+    ref = allp[torch.from_numpy(keep)]
+    ref = ref[ref[:, 4].sort(descending=True)[1][:100]]
+    assert got.shape == ref.shape == (100, 5)
+    assert torch.allclose(got, ref, atol=1e-4)
