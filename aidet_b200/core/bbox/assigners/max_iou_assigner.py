@@ -38,11 +38,13 @@ class MaxIoUAssigner(object):
         >>> gt_bboxes = torch.Tensor([[0, 0, 10, 9]]).cuda()
         >>> assert self.assign(bboxes, gt_bboxes).gt_inds.tolist() == [1, 0]
         """
+        if gt_bboxes.numel() == 0:               # also the shape-(0,) tensor of tests/test_assigner.py:82
+            return self._empty(0, bboxes.size(0), bboxes, gt_labels)
         fmt = gt_bboxes.size(-1)
         assert fmt in (4, 5, 8), 'gt_bboxes must be (k, 4), (k, 5) or (k, 8)'
         bboxes = bboxes[:, :fmt]
         k, n = gt_bboxes.size(0), bboxes.size(0)
-        if k == 0 or n == 0:
+        if n == 0:
             return self._empty(k, n, bboxes, gt_labels)
         if not bboxes.is_cuda:
             raise NotImplementedError('MaxIoUAssigner has no CPU implementation here')

@@ -219,3 +219,38 @@ def test_bbox_mapping_and_aug_merging_on_cpu():
     bb, sc = merge_aug_bboxes([b, m], [torch.ones(1, 2), torch.zeros(1, 2)], metas, None)
     assert torch.allclose(bb, b) and sc.tolist() == [[0.5, 0.5]]
     assert merge_aug_scores([torch.ones(2), torch.zeros(2)]).tolist() == [0.5, 0.5]
+
+
+# ---- the reference's own assigner tests (tests/test_assigner.py:17-162), golden vectors included
+REF_BBOXES = [[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]]
+REF_GTS = [[0, 0, 10, 9], [0, 10, 10, 19]]
+
+
+def test_reference_assigner_goldens_on_the_oracle():
+    b, g = np.array(REF_BBOXES, np.float32), np.array(REF_GTS, np.float32)
+    gi, _, lb = O.max_iou_assign(b, g, 0.5, 0.5, gt_labels=np.array([2, 3]))
+    assert gi.tolist() == [1, 0, 2, 0] and len(lb) == 4                              # test_assigner.py:17-38
+    gi, _, _ = O.max_iou_assign(b, g, 0.5, 0.5, ignore_iof_thr=0.5, ignore_wrt_candidates=False,
+                                gt_bboxes_ignore=np.array([[30, 30, 40, 40]], np.float32))
+    assert gi.tolist() == [1, 0, 2, -1]                                              # test_assigner.py:41-65
+
+
+def test_reference_assigner_empty_cases_on_the_mirror():
+    """tests/test_assigner.py:68-162: no truths, no boxes, neither -- decided on the host, no device needed."""
+    from aidet_b200.core import MaxIoUAssigner
+    a = MaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5)
+    bboxes = torch.FloatTensor(REF_BBOXES)
+    r = a.assign(bboxes, torch.FloatTensor([]))                                      # :68-86
+    assert torch.all(r.gt_inds == torch.LongTensor([0, 0, 0, 0]))
+    gts, labels = torch.FloatTensor(REF_GTS), torch.LongTensor([2, 3])
+    r = a.assign(torch.empty((0, 4)), gts, gt_labels=labels)                         # :89-112
+    assert len(r.gt_inds) == 0 and tuple(r.labels.shape) == (0,)
+    r = a.assign(torch.empty((0, 4)), gts, gt_labels=None)
+    assert len(r.gt_inds) == 0 and r.labels is None
+    ai = MaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5, ignore_iof_thr=0.5)        # :115-148
+    ign = torch.Tensor([[30, 30, 40, 40]])
+    r = ai.assign(torch.empty((0, 4)), gts, gt_labels=labels, gt_bboxes_ignore=ign)
+    assert len(r.gt_inds) == 0 and tuple(r.labels.shape) == (0,)
+    r = ai.assign(torch.empty((0, 4)), gts, gt_labels=None, gt_bboxes_ignore=ign)
+    assert len(r.gt_inds) == 0 and r.labels is None
+    assert len(a.assign(torch.empty((0, 4)), torch.empty((0, 4))).gt_inds) == 0      # :151-162

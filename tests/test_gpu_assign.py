@@ -31,6 +31,18 @@ def test_reference_doctest(cuda):
     assert r.gt_inds.tolist() == [1, 0] and r.num_gts == 1 and r.labels is None
 
 
+def test_reference_assigner_tests(cuda):
+    """The reference's own tests/test_assigner.py:17-65 (golden gt_inds) through the device path."""
+    bboxes = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]]).to(cuda)
+    gts = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]]).to(cuda)
+    r = MaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5).assign(bboxes, gts, gt_labels=torch.LongTensor([2, 3]).to(cuda))
+    assert len(r.gt_inds) == 4 and len(r.labels) == 4
+    assert torch.all(r.gt_inds.cpu() == torch.LongTensor([1, 0, 2, 0])) and r.labels.tolist() == [2, 0, 3, 0]
+    a = MaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5, ignore_iof_thr=0.5, ignore_wrt_candidates=False)
+    r = a.assign(bboxes, gts, gt_bboxes_ignore=torch.Tensor([[30, 30, 40, 40]]).to(cuda))
+    assert torch.all(r.gt_inds.cpu() == torch.LongTensor([1, 0, 2, -1]))
+
+
 @pytest.mark.parametrize("ci", range(N_CFG))
 def test_golden_overlap_matrices(cuda, ci):
     """assign_wrt_overlaps on the reference's matrices (exact ties, -1 columns, an all-zero gt row): bit-exact."""
