@@ -192,7 +192,7 @@ def test_point_obb_gradient_matches_finite_differences(sim_grad, mode, mi, noise
     pred, target = synth.regression_pairs(3000, seed=5)
     a8, b8 = synth.thetaobb2pointobb(pred).numpy(), synth.thetaobb2pointobb(target).numpy()
     rng = np.random.default_rng(2)
-    size = np.sqrt(pred[:, 2] * pred[:, 3]).numpy()[:, None]
+    size = torch.sqrt(pred[:, 2] * pred[:, 3]).numpy()[:, None]
     a8 = (a8 + rng.normal(0, noise, a8.shape) * size).astype(np.float32)
     b8 = (b8 + rng.normal(0, noise, b8.shape) * size).astype(np.float32)
     a8[::2] = a8[::2].reshape(-1, 4, 2)[:, ::-1].reshape(-1, 8)          # clockwise corner order for half of them
