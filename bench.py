@@ -803,7 +803,7 @@ def run_ours(args, D):
                                "(6 kernels), no host read-back; back-to-back calls, L2 warm"},
             "c2": {"eager_us": c2_e, "graph_us": c2_g, "boxes": int(cb2.shape[0]),
                    "workload": "C2: batched rotated NMS of the 15 classes (3 kernels), keep count left on the device"},
-            "how": "CUDA events around 200 back-to-back calls; graph = one torch.cuda.CUDAGraph replayed 200 times"}
+            "how": "CUDA events around %d back-to-back calls; graph = one torch.cuda.CUDAGraph replayed as often" % (5 if args.quick else 200)}
 
     line["clocks"] = sampler.stop() if sampler else None
     line["ffma_peak_tflops_measured"] = ffma
