@@ -1,4 +1,5 @@
+from .approx_max_iou_assigner import ApproxMaxIoUAssigner
 from .assign_result import AssignResult
 from .max_iou_assigner import MaxIoUAssigner
 
-__all__ = ['AssignResult', 'MaxIoUAssigner']
+__all__ = ['AssignResult', 'MaxIoUAssigner', 'ApproxMaxIoUAssigner']

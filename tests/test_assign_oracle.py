@@ -254,3 +254,17 @@ def test_reference_assigner_empty_cases_on_the_mirror():
     r = ai.assign(torch.empty((0, 4)), gts, gt_labels=None, gt_bboxes_ignore=ign)
     assert len(r.gt_inds) == 0 and r.labels is None
     assert len(a.assign(torch.empty((0, 4)), torch.empty((0, 4))).gt_inds) == 0      # :151-162
+
+
+def test_reference_approx_assigner_empty_cases_on_the_mirror():
+    """tests/test_assigner.py:236-297: ApproxMaxIoUAssigner with no truths, no boxes, neither (host-side decisions)."""
+    from aidet_b200.core import ApproxMaxIoUAssigner
+    a = ApproxMaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5)
+    bboxes = torch.FloatTensor(REF_BBOXES)
+    r = a.assign(bboxes, bboxes, 1, torch.FloatTensor([]))
+    assert torch.all(r.gt_inds == torch.LongTensor([0, 0, 0, 0]))
+    e = torch.empty((0, 4))
+    assert len(a.assign(e, e, 1, torch.FloatTensor(REF_GTS)).gt_inds) == 0
+    assert len(a.assign(e, e, 1, torch.empty((0, 4))).gt_inds) == 0
+    with pytest.raises(NotImplementedError):
+        a.assign(bboxes, bboxes, 1, torch.FloatTensor(REF_GTS))
