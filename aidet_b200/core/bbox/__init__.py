@@ -1,6 +1,7 @@
 from .assigners import ApproxMaxIoUAssigner, AssignResult, MaxIoUAssigner
 from .geometry import bbox_overlaps, rbbox_overlaps
-from .transforms import bbox2delta, bbox_flip, bbox_mapping, bbox_mapping_back, delta2bbox
+from .transforms import (bbox2delta, bbox2result, bbox2roi, bbox_flip, bbox_mapping, bbox_mapping_back, delta2bbox,
+                         rbbox2roi, roi2bbox)
 
 __all__ = ['bbox_overlaps', 'rbbox_overlaps', 'AssignResult', 'MaxIoUAssigner', 'ApproxMaxIoUAssigner', 'bbox2delta', 'delta2bbox', 'bbox_flip',
-           'bbox_mapping', 'bbox_mapping_back']
+           'bbox_mapping', 'bbox_mapping_back', 'bbox2roi', 'rbbox2roi', 'roi2bbox', 'bbox2result']

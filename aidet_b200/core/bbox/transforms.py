@@ -2,6 +2,7 @@
 before its NMS.  Tensor ops only (this is the plumbing around the batched NMS launch, not a kernel)."""
 import math
 
+import numpy as np
 import torch
 
 
@@ -79,3 +80,46 @@ def bbox_mapping_back(bboxes, img_shape, scale_factor, flip):
     """Testing scale -> original image scale (transforms.py:142-146)."""
     new_bboxes = bbox_flip(bboxes, img_shape) if flip else bboxes
     return new_bboxes / scale_factor
+
+
+def bbox2roi(bbox_list):
+    """List of per-image (n_i, >=4) boxes -> (n, 5) [batch_ind, x1, y1, x2, y2] RoIs (transforms.py:149-168): the input
+    format of RoIAlign / SingleRoIExtractor."""
+    rois_list = []
+    for img_id, bboxes in enumerate(bbox_list):
+        if bboxes.size(0) > 0:
+            img_inds = bboxes.new_full((bboxes.size(0), 1), img_id)
+            rois = torch.cat([img_inds, bboxes[:, :4]], dim=-1)
+        else:
+            rois = bboxes.new_zeros((0, 5))
+        rois_list.append(rois)
+    return torch.cat(rois_list, 0)
+
+
+def rbbox2roi(rbbox_list):
+    """The same for theta-OBBs: per-image (n_i, >=5) <cx, cy, w, h, theta> -> (n, 6) [batch_ind, cx, cy, w, h, theta], the
+    input format of RoIAlignRotated."""
+    rois_list = []
+    for img_id, rb in enumerate(rbbox_list):
+        if rb.size(0) > 0:
+            rois_list.append(torch.cat([rb.new_full((rb.size(0), 1), img_id), rb[:, :5]], dim=-1))
+        else:
+            rois_list.append(rb.new_zeros((0, 6)))
+    return torch.cat(rois_list, 0)
+
+
+def roi2bbox(rois):
+    """(n, 1 + d) RoIs -> list of per-image (n_i, d) boxes (transforms.py:171-178)."""
+    bbox_list = []
+    for img_id in torch.unique(rois[:, 0].cpu(), sorted=True):
+        bbox_list.append(rois[rois[:, 0] == img_id.item(), 1:])
+    return bbox_list
+
+
+def bbox2result(bboxes, labels, num_classes):
+    """(n, 5) detections + (n,) labels -> list of per-class ndarrays (transforms.py:181-199)."""
+    if bboxes.shape[0] == 0:
+        return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes - 1)]
+    bboxes = bboxes.cpu().numpy()
+    labels = labels.cpu().numpy()
+    return [bboxes[labels == i, :] for i in range(num_classes - 1)]

@@ -268,3 +268,18 @@ def test_reference_approx_assigner_empty_cases_on_the_mirror():
     assert len(a.assign(e, e, 1, torch.empty((0, 4))).gt_inds) == 0
     with pytest.raises(NotImplementedError):
         a.assign(bboxes, bboxes, 1, torch.FloatTensor(REF_GTS))
+
+
+def test_roi_format_helpers_on_cpu():
+    """transforms.py:149-199 and the theta-OBB counterpart that feeds RoIAlignRotated."""
+    from aidet_b200.core import bbox2result, bbox2roi, rbbox2roi, roi2bbox
+    r = bbox2roi([torch.tensor([[1., 2., 3., 4., .9]]), torch.zeros(0, 5), torch.tensor([[5., 6., 7., 8., .1], [1., 1., 2., 2., .5]])])
+    assert r.tolist() == [[0, 1, 2, 3, 4], [2, 5, 6, 7, 8], [2, 1, 1, 2, 2]]
+    back = roi2bbox(r)
+    assert len(back) == 2 and back[1].tolist() == [[5, 6, 7, 8], [1, 1, 2, 2]]
+    rr = rbbox2roi([torch.zeros(0, 6), torch.tensor([[1., 2., 3., 4., .5, .9]])])
+    assert rr.shape == (1, 6) and rr[0].tolist() == [1, 1, 2, 3, 4, .5]
+    assert bbox2roi([torch.zeros(0, 5)]).shape == (0, 5) and rbbox2roi([torch.zeros(0, 5)]).shape == (0, 6)
+    res = bbox2result(torch.tensor([[1., 2., 3., 4., .9], [1., 2., 3., 4., .8]]), torch.tensor([0, 2]), 4)
+    assert [a.shape for a in res] == [(1, 5), (0, 5), (1, 5)]
+    assert [a.shape for a in bbox2result(torch.zeros(0, 5), torch.zeros(0), 3)] == [(0, 5), (0, 5)]
