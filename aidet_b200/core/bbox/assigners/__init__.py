@@ -1,5 +1,4 @@
-from .approx_max_iou_assigner import ApproxMaxIoUAssigner
 from .assign_result import AssignResult
 from .max_iou_assigner import MaxIoUAssigner
 
-__all__ = ['AssignResult', 'MaxIoUAssigner', 'ApproxMaxIoUAssigner']
+__all__ = ['AssignResult', 'MaxIoUAssigner']

@@ -1,6 +1,5 @@
-from .merge_augs import merge_aug_bboxes, merge_aug_proposals, merge_aug_scores
 from .rbbox_nms import (get_det_rbboxes, multiclass_nms, multiclass_nms_with_index, multiclass_thetaobb_nms,
                         thetaobb_nms_by_bbox_nms)
 
 __all__ = ['get_det_rbboxes', 'multiclass_nms', 'multiclass_nms_with_index', 'multiclass_thetaobb_nms',
-           'thetaobb_nms_by_bbox_nms', 'merge_aug_proposals', 'merge_aug_bboxes', 'merge_aug_scores']
+           'thetaobb_nms_by_bbox_nms']

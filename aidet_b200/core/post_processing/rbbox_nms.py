@@ -12,29 +12,41 @@ from ...ops import functional as F
 from ...ops.nms import nms_wrapper
 
 
-def _select(multi_boxes, multi_scores, score_thr, dim):
-    """score filter -> (boxes (m,dim), scores (m,), labels (m,), row index (m,)), class-major order."""
+def _select(multi_boxes, multi_scores, score_thr, dim, class_major=True, score_factors=None):
+    """Score filter on the RAW scores -> (boxes (m,dim), scores (m,), labels (m,)).  class_major=True orders the
+    candidates like the per-class loops of rbbox_nms.py:29-49; False like the boolean indexing of bbox_nms.py:41-47
+    (box by box).  `score_factors` (n,) multiply the scores AFTER the filter, as bbox_nms.py:43-45 does."""
     num_classes = multi_scores.size(1) - 1
     if multi_boxes.shape[1] > dim:
         boxes = multi_boxes.view(multi_scores.size(0), -1, dim)[:, 1:]
     else:
         boxes = multi_boxes[:, None].expand(-1, num_classes, dim)
     scores = multi_scores[:, 1:]
-    valid = (scores > score_thr).t()                  # (C, n): class-major like the reference's loop
-    labels, rows = valid.nonzero(as_tuple=True)
-    return boxes[rows, labels], scores[rows, labels], labels, rows
+    valid = scores > score_thr
+    if score_factors is not None:
+        scores = scores * score_factors[:, None]
+    if class_major:
+        labels, rows = valid.t().nonzero(as_tuple=True)
+    else:
+        rows, labels = valid.nonzero(as_tuple=True)
+    return boxes[rows, labels], scores[rows, labels], labels
 
 
 def _finish(dets, labels, max_num):
-    if max_num > 0 and dets.shape[0] > max_num:       # rbbox_nms.py:52-57 / bbox_nms.py:69-76
+    """bbox_nms.py:69-76 / rbbox_nms.py:52-57, as written there: `if k > max_num: sort by score, [:max_num]`.  With the
+    default max_num = -1 the test is always true, so the reference returns the detections sorted by score WITHOUT THE
+    LAST ONE (`inds[:-1]`); every config passes a positive max_per_img, and the quirk is reproduced, not corrected
+    (tests/golden/golden_postproc_v1.npz holds the reference's outputs for -1, 40 and 100000)."""
+    if dets.shape[0] > max_num:
         _, inds = dets[:, -1].sort(descending=True)
         inds = inds[:max_num]
         dets, labels = dets[inds], labels[inds]
     return dets, labels
 
 
-def _multiclass(multi_boxes, multi_scores, score_thr, iou_thr, max_num, dim, plus_one):
-    boxes, scores, labels, _ = _select(multi_boxes, multi_scores, score_thr, dim)
+def _multiclass(multi_boxes, multi_scores, score_thr, iou_thr, max_num, dim, plus_one, class_major=True,
+                score_factors=None):
+    boxes, scores, labels = _select(multi_boxes, multi_scores, score_thr, dim, class_major, score_factors)
     if boxes.numel() == 0:
         return multi_boxes.new_zeros((0, dim + 1)), multi_boxes.new_zeros((0, ), dtype=torch.long)
     num_classes = multi_scores.size(1) - 1
@@ -44,14 +56,15 @@ def _multiclass(multi_boxes, multi_scores, score_thr, iou_thr, max_num, dim, plu
 
 
 def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None):
-    """mmdet/core/post_processing/bbox_nms.py:6-76.  Returns (bboxes (k,5), labels (k,)), labels 0-based."""
+    """mmdet/core/post_processing/bbox_nms.py:6-76.  Returns (bboxes (k,5), labels (k,)), labels 0-based, in the
+    reference's order (candidates box by box).  The class-offset trick of :57-59 becomes group ids of the batched
+    kernel; `score_factors` scale the scores handed to the NMS and returned, the filter sees the raw scores."""
     cfg = nms_cfg.copy()
     nms_type = cfg.pop('type', 'nms')
     if nms_type != 'nms':
         raise NotImplementedError('multiclass_nms supports type="nms" only (got %r)' % nms_type)
-    if score_factors is not None:
-        multi_scores = torch.cat([multi_scores[:, :1], multi_scores[:, 1:] * score_factors[:, None]], dim=1)
-    return _multiclass(multi_bboxes, multi_scores, score_thr, cfg.get('iou_thr', 0.5), max_num, 4, plus_one=True)
+    return _multiclass(multi_bboxes, multi_scores, score_thr, cfg.get('iou_thr', 0.5), max_num, 4, plus_one=True,
+                       class_major=False, score_factors=score_factors)
 
 
 def multiclass_thetaobb_nms(multi_rbboxes, multi_scores, score_thr, polygon_nms_iou_thr, max_num=-1,
@@ -75,7 +88,7 @@ def multiclass_nms_with_index(multi_bboxes, multi_scores, score_thr, nms_cfg, ma
     num_classes = multi_scores.shape[1]
     valid = multi_scores[:, 1:] > score_thr
     bbox_cls_inds = [valid[:, i] for i in range(num_classes - 1)]
-    boxes, scores, labels, _ = _select(multi_bboxes, multi_scores, score_thr, 4)
+    boxes, scores, labels = _select(multi_bboxes, multi_scores, score_thr, 4)
     if boxes.numel() == 0:
         return (multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0, ), dtype=torch.long), bbox_cls_inds, [])
     keep = F.nms_batched(boxes, scores, labels, cfg.get('iou_thr', 0.5), n_groups=num_classes - 1, cmp_ge=False,
@@ -95,7 +108,9 @@ def multiclass_nms_with_index(multi_bboxes, multi_scores, score_thr, nms_cfg, ma
 
 
 def thetaobb_nms_by_bbox_nms(multi_bboxes, multi_scores, bbox_cls_inds, bbox_keep_inds, max_num=-1, out_dim_reg=5):
-    """mmdet/core/post_processing/rbbox_nms.py:64-119: gather OBBs with the keep indices of the HBB NMS."""
+    """mmdet/core/post_processing/rbbox_nms.py:64-119: gather OBBs with the keep indices of the HBB NMS (the slot
+    where the reference left its rotated NMS commented out, :97-98; `multiclass_thetaobb_nms` is that call).  The
+    reference pops `bbox_keep_inds` empty (:99); the caller's list is left alone here."""
     num_classes = multi_scores.shape[1]
     bboxes, labels = [], []
     keep_iter = iter(bbox_keep_inds)
@@ -143,8 +158,10 @@ def get_det_rbboxes(rois, cls_score, rbbox_pred, img_shape, scale_factor, rescal
         cls_score = sum(cls_score) / float(len(cls_score))
     scores = TF.softmax(cls_score, dim=1) if cls_score is not None else None
     if rbbox_pred is not None:
-        means = tuple(target_means) if len(target_means) == dim else (0.,) * dim
-        stds = tuple(target_stds) if len(target_stds) == dim else (1.,) * dim
+        if len(target_means) != dim or len(target_stds) != dim:
+            raise ValueError("encode=%r decodes %d deltas per box: target_means / target_stds must have %d entries, got %d / %d"
+                             % (encode, dim, dim, len(target_means), len(target_stds)))
+        means, stds = tuple(target_means), tuple(target_stds)
         rbboxes = decode[encode](rois[:, 1:], rbbox_pred, means, stds, img_shape)
     else:
         rbboxes = rois[:, 1:]

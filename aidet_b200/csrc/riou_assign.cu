@@ -30,13 +30,15 @@ namespace aidet {
 constexpr int kACols = 256;
 constexpr int kARows = 64;
 
-// Overlaps are >= 0 (or -1 = "ignored" in a caller-provided matrix): v >= 0 -> bits + 1, anything else -> 0, so
-// unsigned order == float order and 0 means "no value" (the reference's -1).
+// Overlaps are >= 0 (or -1 = "ignored" in a caller-provided matrix): v > 0 -> bits + 1, +-0 -> 1, anything else
+// (negative, NaN) -> 0, so unsigned order == float order and 0 means "no value" (the reference's -1).  Both zeros
+// map to the same code: the bits of -0.0f (0x80000000) would otherwise rank above every positive overlap.
 __host__ __device__ __forceinline__ unsigned ov_enc(float v) {
 #if defined(__CUDA_ARCH__)
-  return v >= 0.0f ? __float_as_uint(v) + 1u : 0u;
+  return v > 0.0f ? __float_as_uint(v) + 1u : (v == 0.0f ? 1u : 0u);
 #else
-  if (!(v >= 0.0f)) return 0u;
+  if (v == 0.0f) return 1u;
+  if (!(v > 0.0f)) return 0u;
   union { float f; unsigned u; } x; x.f = v; return x.u + 1u;
 #endif
 }

@@ -570,51 +570,6 @@ def run_ours(args, D):
                           "h2d_bytes_per_step": int(cb.numel() * 4 + cs.numel() * 4 + cg.numel() * 4),
                           "d2h_bytes_per_step": int(kk.numel() * 8 + 4), "ms_per_step": ems / args.steps,
                           "how": "c2: pinned host boxes/scores/groups -> batched_rnms -> keep indices on the host"}
-        # ---- RPN proposal stage (caller of nms: rpn_head.py:55-108): 8 images x 5 levels, nms_pre 2000, thr 0.7
-        from aidet_b200.models.anchor_heads.rpn_head import decode_levels, select_proposals
-        from aidet_b200.ops import nms as nms_op
-        rg = torch.Generator().manual_seed(31)
-        r_img, r_tile, r_str = 8, 1024, (4, 8, 16, 32, 64)
-        r_cls = [(torch.randn(r_img, 3, r_tile // s_, r_tile // s_, generator=rg) * 2).to(dev) for s_ in r_str]
-        r_reg = [(torch.randn(r_img, 12, r_tile // s_, r_tile // s_, generator=rg) * 0.4).to(dev) for s_ in r_str]
-        r_anc = []
-        for s_ in r_str:
-            a_ = synth.anchor_grid(tile=r_tile, strides=(s_,))
-            r_anc.append(torch.cat([a_[:, :2] - a_[:, 2:4] / 2 + 0.5, a_[:, :2] + a_[:, 2:4] / 2 - 0.5], 1).to(dev))
-        r_cfg = dict(nms_across_levels=False, nms_pre=2000, nms_post=2000, max_num=2000, nms_thr=0.7, min_bbox_size=0)
-        r_shapes = [(r_tile, r_tile, 3)] * r_img
-        r_props, r_gids = decode_levels(r_cls, r_reg, r_anc, r_shapes, r_cfg)
-        r_ng = r_img * len(r_str)
-
-        def rpn_select():
-            return select_proposals(r_props, r_gids, r_img, len(r_str), r_cfg)
-
-        def rpn_loop():           # the reference's structure: one nms() call per (image, level), then cat + top-k
-            outs = []
-            for i_ in range(r_img):
-                lv_ = []
-                for l_ in range(len(r_str)):
-                    p_ = r_props[r_gids == l_ * r_img + i_]
-                    d_, _ = nms_op(p_, 0.7)
-                    lv_.append(d_[:2000])
-                p_ = torch.cat(lv_, 0)
-                outs.append(p_[p_[:, 4].topk(min(2000, p_.shape[0]))[1]])
-            return outs
-
-        L.prof_read(L.PROF_NMS_MASK, reset=True)
-        rms, rl = timed(D, dev, args.steps, args.warmup, rpn_select, flush=flush)
-        rk_ms, rk_cnt = L.prof_read(L.PROF_NMS_MASK, reset=True)
-        lms = float('nan')
-        if not args.quick:
-            lms, _ = timed(D, dev, max(2, args.steps // 3), 1, rpn_loop, flush=flush)
-        r_pairs = group_pairs(r_gids.cpu(), r_ng)
-        nms["rpn"] = {"value": r_props.shape[0] * G / (rms / args.steps) / 1e3, "unit": "Mboxes/s", "ms_per_step": rms / args.steps,
-                      "boxes": int(r_props.shape[0]), "groups": r_ng, "gpu_launches": int(rl),
-                      "per_level_loop_ms": None if args.quick else lms / max(2, args.steps // 3),
-                      "mask_kernel_ms": rk_ms / max(rk_cnt, 1),
-                      "workload": "RPN proposal selection (rpn_head.py:94-108) for 8 images x 5 FPN levels of a 1024 tile: HBB NMS "
-                                  "@0.7 (+1) of the top-2000 per (image, level) in ONE batched launch, [:nms_post], per-image top-2000; "
-                                  "per_level_loop = the same with one nms() call per (image, level); charged pairs %d" % r_pairs}
         line["nms"] = nms
 
     # ---------------- rotated RoIAlign fwd + bwd (C3)

@@ -78,7 +78,7 @@ def test_python_surface_matches_reference_names():
     assert list(inspect.signature(core.rbbox_overlaps).parameters) == ["rbboxes1", "rbboxes2", "mode", "is_aligned"]
     assert list(inspect.signature(core.multiclass_thetaobb_nms).parameters)[:5] == [
         "multi_rbboxes", "multi_scores", "score_thr", "polygon_nms_iou_thr", "max_num"]
-    # max_iou_assigner.py:37-44, iou_loss.py:131, rpn_head.py:55-62, transforms.py:34-39
+    # max_iou_assigner.py:37-44, iou_loss.py:131
     assert list(inspect.signature(core.MaxIoUAssigner.__init__).parameters) == [
         "self", "pos_iou_thr", "neg_iou_thr", "min_pos_iou", "gt_max_assign_all", "ignore_iof_thr", "ignore_wrt_candidates",
         "gpu_assign_thr"]
@@ -86,9 +86,12 @@ def test_python_surface_matches_reference_names():
         "self", "bboxes", "gt_bboxes", "gt_bboxes_ignore", "gt_labels"]
     from aidet_b200 import models
     assert list(inspect.signature(models.RotatedIoULoss.__init__).parameters) == ["self", "eps", "reduction", "loss_weight"]
-    assert list(inspect.signature(models.rpn_get_bboxes_single).parameters)[:7] == [
-        "cls_scores", "bbox_preds", "mlvl_anchors", "img_shape", "scale_factor", "cfg", "rescale"]
-    assert list(inspect.signature(core.delta2bbox).parameters) == ["rois", "deltas", "means", "stds", "max_shape", "wh_ratio_clip"]
+    # core/rbbox/transforms.py:191,398,405 and rbbox_target.py:8-17
+    assert list(inspect.signature(core.thetaobb_flip).parameters) == ["thetaobbs", "img_shape"]
+    assert list(inspect.signature(core.thetaobb_mapping_back).parameters) == ["thetaobbs", "img_shape", "scale_factor", "flip"]
+    assert list(inspect.signature(core.rbbox_target).parameters) == [
+        "pos_proposals_list", "neg_proposals_list", "pos_assigned_gt_inds_list", "gt_rbboxes_list", "gt_labels_list",
+        "rbbox_test_cfg", "target_means", "target_stds", "out_dim_reg", "concat"]
 
 
 def test_no_cpu_fallback():

@@ -142,26 +142,18 @@ def test_scores_column_is_dropped_and_errors(cuda):
         a.assign(boxes.to(cuda), torch.rand(3, 6).to(cuda))
 
 
-def test_approx_max_iou_assigner(cuda):
-    """tests/test_assigner.py:211-233 (golden) and a 9-approximations case against the reference procedure
-    (approx_max_iou_assigner.py:99-131) restated on the float64 oracle overlaps."""
-    from aidet_b200.core import ApproxMaxIoUAssigner
-    bboxes = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]]).to(cuda)
-    gts = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]]).to(cuda)
-    r = ApproxMaxIoUAssigner(pos_iou_thr=0.5, neg_iou_thr=0.5).assign(bboxes, bboxes, 1, gts)
-    assert torch.all(r.gt_inds.cpu() == torch.LongTensor([1, 0, 2, 0]))
-    # 400 squares x 9 theta-OBB approximations (scaled / turned copies of the square), 20 truths, ignore boxes
-    sq, gt, ign, labels = synth.assign_case(400, 20, side=512, seed=77, n_ignore=3)
-    g = torch.Generator().manual_seed(5)
-    ap = sq[:, None, :].repeat(1, 9, 1)
-    ap[:, :, 2:4] *= torch.rand(400, 9, 2, generator=g) * 0.8 + 0.6
-    ap[:, :, 4] += torch.randn(400, 9, generator=g) * 0.2
-    ap = ap.reshape(-1, 5).contiguous()
-    a = ApproxMaxIoUAssigner(0.5, 0.4, 0.2, True, ignore_iof_thr=0.5, ignore_wrt_candidates=True)
-    r = a.assign(ap.to(cuda), sq.to(cuda), 9, gt.to(cuda), ign.to(cuda), labels.to(cuda))
-    ov = O.riou_matrix(ap.numpy(), gt.numpy()).reshape(400, 9, 20).max(1).T.copy()           # (k, n)
-    ov[:, O.riou_matrix(sq.numpy(), ign.numpy(), mode="iof").max(1) > 0.5] = -1
-    gi, mo, lb = O.max_iou_assign_wrt_overlaps(ov, 0.5, 0.4, 0.2, True, labels.numpy())
-    got = r.gt_inds.cpu().numpy()
-    assert np.abs(r.max_overlaps.cpu().numpy() - mo).max() <= 1e-5
-    assert (got != gi).mean() <= 5e-3 and (got > 0).sum() > 20
+
+@pytest.mark.gpu
+def test_negative_zero_entries_in_a_caller_matrix(cuda):
+    """-0.0 is a legal overlap value in assign_wrt_overlaps: it must rank as 0, not above every positive entry (its
+    bits are 0x80000000), exactly as the numpy restatement of max_iou_assigner.py:122-195 ranks it."""
+    rng = np.random.default_rng(3)
+    ov = (np.round(rng.uniform(0, 1, (6, 200)) * 10) / 10).astype(np.float32)
+    ov[:, ::7] = -0.0
+    ov[2] = np.where(np.arange(200) % 2 == 0, -0.0, 0.0).astype(np.float32)          # a truth whose best overlap is zero
+    lab = np.arange(1, 7)
+    a = MaxIoUAssigner(0.5, 0.4, 0.0, True)
+    r = a.assign_wrt_overlaps(torch.from_numpy(ov).to(cuda), torch.from_numpy(lab).to(cuda))
+    gi, mo, lb = O.max_iou_assign_wrt_overlaps(ov, 0.5, 0.4, 0.0, True, lab)
+    assert np.array_equal(r.gt_inds.cpu().numpy(), gi) and np.array_equal(r.labels.cpu().numpy(), lb)
+    assert np.array_equal(r.max_overlaps.cpu().numpy(), np.abs(mo))                   # -0.0 == 0.0 by value
