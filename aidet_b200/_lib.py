@@ -105,7 +105,9 @@ def require_cuda(t, name):
 
 
 def prof_enable(on=True):
-    check(lib().aidet_prof_enable(int(bool(on))), "aidet_prof_enable")
+    """0 / False: off; 1 / True: CUDA-event timing of the dominant kernel of each op; 2: also the phase stamps of the
+    fused NMS kernel (left at the end of its workspace, scripts/r2_nms_phases.py)."""
+    check(lib().aidet_prof_enable(int(on)), "aidet_prof_enable")
 
 
 def prof_read(kind, reset=True):

@@ -12,7 +12,7 @@ namespace aidet {
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
-static bool g_prof_on = false;
+static int g_prof_level = 0;          // 0 off, 1 per-op kernel timing, 2 + phase stamps of the fused NMS kernel
 static std::mutex g_mu;
 struct EvPair { cudaEvent_t e0, e1; };
 static std::vector<EvPair> g_pending[PROF_KINDS];
@@ -28,7 +28,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 void count_launch(int n) { std::lock_guard<std::mutex> l(g_mu); g_launches += n; }
 
-ProfScope::ProfScope(int kind_, cudaStream_t s_) : kind(kind_), s(s_), on(g_prof_on), e0(nullptr), e1(nullptr) {
+int prof_level() { return g_prof_level; }
+
+ProfScope::ProfScope(int kind_, cudaStream_t s_) : kind(kind_), s(s_), on(g_prof_level > 0), e0(nullptr), e1(nullptr) {
   if (!on) return;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { on = false; return; }
   cudaEventRecord(e0, s);
@@ -81,7 +83,7 @@ const char* aidet_last_error(void) { return g_err; }
 int aidet_version(void) { return 100; }
 long long aidet_launch_count(void) { std::lock_guard<std::mutex> l(g_mu); return g_launches; }
 
-int aidet_prof_enable(int enable) { g_prof_on = enable != 0; return AIDET_OK; }
+int aidet_prof_enable(int enable) { g_prof_level = enable < 0 ? 0 : enable; return AIDET_OK; }
 
 int aidet_prof_read(int kind, double* ms_total, long long* launches, int reset) {
   AIDET_REQUIRE(kind >= 0 && kind < PROF_KINDS, "aidet_prof_read: kind %d out of range", kind);

@@ -73,6 +73,23 @@ __global__ void __launch_bounds__(256) riou_prepare_kernel(const float* __restri
   if (cols) cols[i] = c;
 }
 
+// both sides of a matrix in ONE launch: threads [0, m) prepare the row records of `a`, threads [m, m + n) the column
+// records of `b` (small problems are launch bound: C1 is a 2000 x 2000 matrix)
+template <class K>
+__global__ void __launch_bounds__(256) riou_prepare_both_kernel(const float* __restrict__ a, int m, const float* __restrict__ b,
+                                                                int n, typename K::Row* rows, typename K::Col* cols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m + n) return;
+  const bool is_row = i < m;
+  const float* src = is_row ? a + (size_t)i * K::FMT : b + (size_t)(i - m) * K::FMT;
+  float v[K::FMT];
+#pragma unroll
+  for (int k = 0; k < K::FMT; k++) v[k] = src[k];
+  typename K::Row r; typename K::Col c;
+  K::prepare(v, is_row ? &r : nullptr, is_row ? nullptr : &c);
+  if (is_row) rows[i] = r; else cols[i - m] = c;
+}
+
 static inline size_t record_bytes(int fmt) { return (fmt == 8) ? 64 : (fmt == 4 ? 16 : 32); }
 
 }  // namespace aidet

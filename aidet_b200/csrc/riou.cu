@@ -201,8 +201,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   using S = typename P::S; using R = typename P::R;
   S* rows = reinterpret_cast<S*>(ws);
   R* cols = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)m * sizeof(S), 128));
-  riou_prepare_kernel<K><<<ceil_div(m, 256), 256, 0, s>>>(a, m, rows, nullptr);
-  riou_prepare_kernel<K><<<ceil_div(n, 256), 256, 0, s>>>(b, n, nullptr, cols);
+  riou_prepare_both_kernel<K><<<ceil_div(m + n, 256), 256, 0, s>>>(a, m, b, n, rows, cols);
   const int sms = sm_count(device);
   const int n_col_tiles = ceil_div(n, kColsPerTile);
   int tile_rows = kMaxTileRows;
@@ -226,7 +225,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
     else                 { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_LOCAL); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_LOCAL); }
 #undef AIDET_LAUNCH_RIOU
   }
-  count_launch(3);
+  count_launch(2);
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;
 }

@@ -17,6 +17,7 @@
 // Up to 8192 boxes (every per-image config) steps 1-2 are ONE kernel (rank by counting) and the tile
 // prefix is computed inside the mask kernel: 3 launches per call.
 // Bound: step 3, FP32 issue (same pair arithmetic as riou.cu); steps 1,2,4,5 are latency.
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <stdlib.h>
@@ -529,6 +530,480 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(const uint8_t* __rest
   if (threadIdx.x == 1023) *n_keep = off;
 }
 
+// ------------------------------------------------------------------ fused path (n <= 8192)
+// Per-image problems (config C1: 2000 boxes in one group; C2: ~5800 boxes in 15 classes) hold a few microseconds of
+// arithmetic, so three dependent launches with their ramp-up, per-CTA prologues and ticket atomics cost far more
+// than the work (r1: C2 52 us, C1 138 us under graph replay).  ONE cooperative launch runs all phases, separated
+// by two grid barriers:
+//   rank   the CTAs that own boxes bucket all keys by group in shared memory (histogram + cursor atomics, warp
+//          aggregated), so a box is ranked against its own group only (rank = sorted position: group, score
+//          descending, index ascending); lanes 0-7 of a warp prepare the records of its 8 boxes and store them to
+//          their sorted slots
+//   mask   warp-level units: 32 columns (one record per lane, in registers) x RC rows (records read with
+//          warp-uniform loads), only units at or above the diagonal are enumerated; a CTA takes a contiguous run
+//          of units (same group, same strip: rows hit L1, the column record is reused) and its warps draw from it
+//          through a shared-memory counter -- no staging, no CTA barrier, no global ticket.  The words of a 32-row
+//          block are stored [word][row]: a coalesced 128-byte store per unit, one contiguous run per block
+//   scan   one CTA per group, warp-specialised: warp 0 runs the greedy chain on the 32x32 diagonal block and takes
+//          the contribution of a block to the NEXT three words itself (predicated ORs inside the chain's empty issue
+//          slots); warp 1 streams the following blocks into a shared-memory ring, ONE TMA bulk copy (cp.async.bulk
+//          + mbarrier) per block; warps 2-7 OR the kept rows into the words four and more blocks ahead (one redux.or
+//          per word, each word owned by a fixed warp: no atomics).  The chain never meets a CTA barrier: a step costs
+//          its 32 dependent bit decisions (taken two at a time), and blocks whose rows are all suppressed already
+//          cost neither a chain nor a wait for their data
+//   compact  by the CTA that finishes last.
+namespace cg = cooperative_groups;
+
+constexpr int kFusedMaxBoxes = 8192;
+constexpr int kFusedMaxGroups = 1024;
+constexpr int kFusedThreads = 256;
+constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp unit
+constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
+constexpr int kScanHelpers = kFusedThreads / 32 - 2;
+constexpr int kPanelBlocks = 64;           // groups of <= 64 blocks (2048 boxes): the chain's words live in a 32 KB panel
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v;
+}
+
+// units of a group with ng boxes: strips of 32 columns c = 0..ns-1, strip c needs rows 0 .. min(ng, 32c+32)-1 (every row
+// that precedes one of its columns, plus the rest of the diagonal block so that all of its words get written) in
+// chunks of RC rows: (c+1) * 32/RC units, the last strip ceil(ng / RC)
+__host__ __device__ __forceinline__ int fused_units(int ng, int q /* 32 / RC */, int rc) {
+  if (ng <= 0) return 0;
+  const int ns = (ng + 31) >> 5;
+  return q * ((ns - 1) * ns / 2) + (ng + rc - 1) / rc;
+}
+
+// key of box j inside its group: better boxes have smaller keys (score descending, then index ascending)
+__device__ __forceinline__ uint64_t bucket_key(const float* __restrict__ scores, int j) {
+  return ((uint64_t)(~orderable(__ldg(scores + j))) << 13) | (uint64_t)j;
+}
+__device__ __forceinline__ int bucket_group(const int* __restrict__ groups, int j, int n_groups) {
+  const uint32_t g = groups ? (uint32_t)__ldg(groups + j) : 0u;
+  return (int)min(g, (uint32_t)n_groups);     // ids outside [0, n_groups) go to a bucket behind every group: never scanned
+}
+
+// 4 resident CTAs per SM (64 registers) for the 32-byte record kinds, 3 for the 64-byte quad records
+template <class O, bool GE>
+__global__ void __launch_bounds__(kFusedThreads, O::FMT == 8 ? 3 : 4)
+nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ groups,
+                 int n, int n_groups, const float* __restrict__ thr, int n_thr, float one, int rc_rows,
+                 typename O::Row* rows, typename O::Col* cols, int* order, uint8_t* flags, int* gstart, int* gend,
+                 int* done, int* ticket, uint32_t* mask32, long long pitch32, int ring_words,
+                 long long* __restrict__ keep_out, int* __restrict__ n_keep, long long* __restrict__ stamps) {
+  using Row = typename O::Row; using Col = typename O::Col;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  // phase-2 tables (unit prefix, group starts / ends) live in the dynamic shared memory, which is free between the
+  // key array of phase 1 and the ring of phase 3: (n_groups + 2) ints each
+  int* const sprefix = reinterpret_cast<int*>(dyn);
+  int* const sstart = sprefix + (n_groups + 2);
+  int* const send = sstart + (n_groups + 2);
+  __shared__ int swarp[8];
+  __shared__ __align__(8) uint64_t bar_full[kScanSlotsMax], bar_k[kScanSlotsMax];
+  __shared__ uint32_t s_issued;              // blocks whose copy the producer has issued
+  __shared__ uint32_t s_hprog[8];            // blocks finished by each helper warp (written by its lane 0 only)
+  __shared__ uint32_t s_keep[kFusedMaxBoxes / 32], s_removed[kFusedMaxBoxes / 32];
+  __shared__ int s_last;
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kFusedThreads / 32;
+  // diagnostics (aidet_prof_enable(2); stamps == nullptr otherwise): phase time stamps of CTA 0 (SM clock) in stamps[0..7],
+  // and in stamps[16 + k] the LATEST arrival of any CTA at boundary k (global nanosecond timer; [16] = negated EARLIEST start),
+  // left at the end of the workspace for scripts/r2_nms_phases.py
+  auto stamp = [&](int k) {
+    if (stamps && tid == 0) {
+      if (blockIdx.x == 0) stamps[k] = clock64();
+      if (k < 8) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMax(reinterpret_cast<unsigned long long*>(stamps) + 16 + k, k == 0 ? ~t : t);
+      }
+    }
+  };
+  stamp(0);
+
+  // exclusive prefix of v(g), g < count, into sprefix[0..count] (all threads call; count <= kFusedMaxGroups + 1)
+  auto cta_prefix = [&](auto value_of, int count) {
+    int carry = 0;
+    for (int base = 0; base < count; base += kFusedThreads) {
+      const int g = base + tid;
+      const int v = (g < count) ? value_of(g) : 0;
+      int x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+      if (lane == 31) swarp[warp] = x;
+      __syncthreads();
+      int wsum = 0, tot = 0;
+      for (int w = 0; w < kWarps; ++w) { const int sw = swarp[w]; if (w < warp) wsum += sw; tot += sw; }
+      if (g < count) sprefix[g] = carry + wsum + x - v;
+      carry += tot;
+      __syncthreads();
+    }
+    if (tid == 0) sprefix[count] = carry;
+    __syncthreads();
+  };
+
+  // ---------------------------------------------------------------- phase 1: rank + prepare + group bounds
+  {
+    // every CTA that owns units keeps ALL keys in shared memory.  The loads are issued in batches of 8 per thread
+    // before the first key is built (a plain loop exposes one L2 latency per iteration: 23 of them at config C2)
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(dyn);
+    const int u_box = (n + kRankBoxes - 1) / kRankBoxes, u_all = u_box + n_groups + 1;
+    const int ctas_p1 = min((int)gridDim.x, (u_all + kWarps - 1) / kWarps);
+    if (blockIdx.x == 0 && tid == 0) { *done = 0; *ticket = 0; }
+    if ((int)blockIdx.x < ctas_p1) {
+      for (int j0 = 0; j0 < n; j0 += 8 * kFusedThreads) {
+        float sc[8]; int gr[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = j0 + k * kFusedThreads + tid;
+          sc[k] = (j < n) ? __ldg(scores + j) : 0.f;
+          gr[k] = (j < n && groups) ? __ldg(groups + j) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = j0 + k * kFusedThreads + tid;
+          if (j < n) {
+            const uint32_t g = min((uint32_t)gr[k], (uint32_t)n_groups);   // ids outside [0, n_groups): behind every group, never scanned
+            skeys[j] = ((uint64_t)g << kRankGroupShift) | ((uint64_t)(~orderable(sc[k])) << 13) | (uint64_t)j;
+          }
+        }
+      }
+      __syncthreads();
+      // Candidates usually arrive class by class (multiclass_nms builds them that way): when the group ids are
+      // non-decreasing a group is a contiguous index range, so a box is ranked against its own group only and the
+      // group bounds fall out of the boundary search -- 15x less counting at config C2.  Both paths give the same order.
+      int* gfirst = reinterpret_cast<int*>(skeys + n);                 // [n_groups + 1] first index / one past the last index
+      int* glast = gfirst + (n_groups + 1);
+      for (int g = tid; g <= n_groups; g += kFusedThreads) { gfirst[g] = 0; glast[g] = 0; }
+      __syncthreads();
+      int unsorted = 0;
+      for (int j = tid; j < n; j += kFusedThreads) {
+        const int gj = (int)(skeys[j] >> kRankGroupShift), gp = j ? (int)(skeys[j - 1] >> kRankGroupShift) : -1;
+        unsorted |= gj < gp;
+        if (gj != gp) { gfirst[gj] = j; if (j) glast[gp] = j; }
+        if (j == n - 1) glast[gj] = n;
+      }
+      const bool sorted = !__syncthreads_or(unsorted);
+      stamp(13);
+      if (sorted && blockIdx.x == 0)
+        for (int g = tid; g < n_groups; g += kFusedThreads) { gstart[g] = gfirst[g]; gend[g] = glast[g]; }
+      const int n_p1warps = ctas_p1 * kWarps;
+      for (int u = blockIdx.x * kWarps + warp; u < (sorted ? u_box : u_all); u += n_p1warps) {
+        if (u < u_box) {
+          const int i0 = u * kRankBoxes, mine = i0 + lane;
+          // lanes 0..3 prepare the unit's boxes first: the FP64 sincos of rect_prepare overlaps the other warps' counting
+          Row r; Col cc;
+          if (lane < kRankBoxes && mine < n) {
+            float bx[O::FMT];
+#pragma unroll
+            for (int k = 0; k < O::FMT; k++) bx[k] = __ldg(boxes + (size_t)mine * O::FMT + k);
+            O::prepare(bx, one, &r, &cc);
+          }
+          uint64_t ki[kRankBoxes];
+#pragma unroll
+          for (int b = 0; b < kRankBoxes; ++b) ki[b] = (i0 + b < n) ? skeys[i0 + b] : 0ull;
+          // sorted: the unit's boxes lie in groups g_first .. g_last, whose members are the indices [j_lo, j_hi); every key
+          // before j_lo is smaller than theirs (lower group), every key from j_hi on larger
+          int j_lo = 0, j_hi = n;
+          if (sorted) {
+            j_lo = gfirst[(int)(ki[0] >> kRankGroupShift)];
+            j_hi = glast[(int)(skeys[min(i0 + kRankBoxes, n) - 1] >> kRankGroupShift)];
+          }
+          int c[kRankBoxes] = {0, 0, 0, 0};
+#pragma unroll 4
+          for (int j = j_lo + lane; j < j_hi; j += 32) {
+            const uint64_t kj = skeys[j];
+#pragma unroll
+            for (int b = 0; b < kRankBoxes; ++b) c[b] += (kj < ki[b]) ? 1 : 0;
+          }
+#pragma unroll
+          for (int b = 0; b < kRankBoxes; ++b) c[b] = __reduce_add_sync(0xffffffffu, c[b]);
+          if (lane < kRankBoxes && mine < n) {
+            int rank = c[0];
+#pragma unroll
+            for (int b = 1; b < kRankBoxes; ++b) if (lane == b) rank = c[b];
+            rank += j_lo;
+            order[rank] = mine;
+            flags[mine] = 0;
+            rows[rank] = r;
+            if constexpr (!std::is_same<Row, Col>::value) cols[rank] = cc;
+          }
+        } else {
+          const int g = u - u_box;                                     // first sorted position of group g (g == n_groups: end)
+          const uint64_t kg = (uint64_t)g << kRankGroupShift;
+          int cnt = 0;
+          for (int j = lane; j < n; j += 32) cnt += (skeys[j] < kg) ? 1 : 0;
+          cnt = __reduce_add_sync(0xffffffffu, cnt);
+          if (lane == 0) {
+            if (g < n_groups) gstart[g] = cnt;
+            if (g > 0) gend[g - 1] = cnt;
+          }
+        }
+      }
+    }
+  }
+  stamp(1);
+  grid.sync();
+  stamp(2);
+
+  // ---------------------------------------------------------------- phase 2: suppression mask, warp-level units
+  const int q = 32 / rc_rows;
+  {
+    // unit prefix over the groups; group starts / sizes / thresholds stay in shared memory (no L2 round trip per unit)
+    for (int g = tid; g < n_groups; g += kFusedThreads) { sstart[g] = __ldcg(gstart + g); send[g] = __ldcg(gend + g); }
+    __syncthreads();
+    cta_prefix([&](int g) { return fused_units(send[g] - sstart[g], q, rc_rows); }, n_groups);
+    const int total = sprefix[n_groups];
+    // static, interleaved: run r = units 8r .. 8r+7 (one per warp: same strip as a rule, so the column record is
+    // fetched from L2 once per CTA) goes to CTA r % grid -- neighbouring runs cost alike (same group, same place in the
+    // image), so dealing them out round-robin balances the CTAs without a work counter
+    int u = blockIdx.x * kWarps + warp;
+    const int u_hi = total, u_step = gridDim.x * kWarps;
+    int cur_g = -1, cur_c = -1, start = 0, ng = 0;
+    Col me; float area_me = 0.f, th = 0.f; bool zero_hit = false;
+    while (u < u_hi) {
+      int lo = 0, hi = n_groups;                                     // last g with sprefix[g] <= u
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sprefix[mid] <= u) lo = mid; else hi = mid; }
+      const int g = lo;
+      if (g != cur_g) { start = sstart[g]; ng = send[g] - start; }
+      const int ns = (ng + 31) >> 5;
+      const int l = u - sprefix[g];
+      // strip c: the largest c with q c (c+1) / 2 <= l, capped at ns - 1
+      int c = (int)((sqrtf(8.0f * (float)l / (float)q + 1.0f) - 1.0f) * 0.5f);
+      c = min(c, ns - 1);
+      while (c > 0 && q * (c * (c + 1) / 2) > l) --c;
+      while (c < ns - 1 && q * ((c + 1) * (c + 2) / 2) <= l) ++c;
+      const int r0 = (l - q * (c * (c + 1) / 2)) * rc_rows;
+      const int c0 = c << 5;
+      const int r_end = min(min(ng, c0 + 32), r0 + rc_rows);
+      const int j = c0 + lane;
+      const bool live = j < ng;
+      if (g != cur_g || c != cur_c) {
+        me = cols[start + (live ? j : ng - 1)];
+        area_me = O::area_c(me, one);
+        th = __ldg(thr + (n_thr == 1 ? 0 : g));
+        zero_hit = GE ? (0.0f >= th) : (0.0f > th);
+        cur_g = g; cur_c = c;
+      }
+      const Row* rr = rows + start;
+      uint32_t word = 0;
+#pragma unroll 2
+      for (int i = r0; i < r_end; ++i) {
+        const Row a = rr[i];                                          // warp-uniform address: one transaction, L1 hit after the first unit
+        const bool hit = nms_hit<O, GE>(a, me, area_me, one, th, zero_hit);
+        const uint32_t bb = __ballot_sync(0xffffffffu, hit && live && j > i);
+        if (lane == (i & 31)) word = bb;
+      }
+      // rows r0 .. r_end-1 live in one 32-row block (rc_rows divides 32): lane (i & 31) holds row i's word.
+      // Blocked layout: word (block b, word c, row r) of the group at ((b * pitch32 + c) * 32 + r).
+      const int i_mine = (r0 & ~31) + lane;
+      if (i_mine >= r0 && i_mine < r_end)
+        mask32[(long long)(start + 32 * g) * pitch32 + ((long long)(r0 >> 5) * pitch32 + c) * 32 + lane] = word;
+      u += u_step;
+    }
+  }
+  stamp(3);
+  grid.sync();
+  stamp(4);
+
+  // ---------------------------------------------------------------- phase 3: greedy scan, one CTA per group
+  uint32_t* ring = reinterpret_cast<uint32_t*>(dyn);
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int start = __ldcg(gstart + g), ng = __ldcg(gend + g) - start;
+    if (ng <= 0) continue;
+    const int nhw = (ng + 31) >> 5;
+    const int slot_words = 32 * nhw;
+    // groups of <= 2048 boxes keep words b .. b+3 of every block b (all the chain reads) in a 32 KB panel at the end
+    // of the dynamic shared memory, loaded once; the ring then only feeds the helpers
+    const bool use_panel = nhw <= kPanelBlocks && (ring_words - nhw * 128) / slot_words >= 2;
+    uint32_t* panel = ring + (ring_words - nhw * 128);
+    const int D = min(kScanSlotsMax, (use_panel ? ring_words - nhw * 128 : ring_words) / slot_words);   // >= 2 (host)
+    const uint32_t* mgrp = mask32 + (long long)(start + 32 * g) * pitch32;
+    __syncthreads();                                                   // previous group done with the barriers / s_keep
+    if (tid < kScanSlotsMax) { mbar_init(&bar_full[tid], 1); mbar_init(&bar_k[tid], 1); fence_barrier_init(); }
+    for (int h = tid; h < nhw; h += kFusedThreads) { s_removed[h] = 0u; s_keep[h] = 0u; }
+    if (tid < 8) s_hprog[tid] = 0u;
+    if (tid == 8) s_issued = 0u;
+    if (use_panel) {
+      // block b: its words b .. b+3 are 128 consecutive words of the blocked layout -> one 16-byte load per lane
+#pragma unroll 8
+      for (int b = warp; b < nhw; b += kWarps) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (b + (lane >> 3) < nhw) v = __ldcg(reinterpret_cast<const uint4*>(mgrp + ((long long)b * pitch32 + b) * 32) + lane);
+        reinterpret_cast<uint4*>(panel + b * 128)[lane] = v;
+      }
+    }
+    __syncthreads();
+    if (warp == 1) {
+      // ---- producer: block b = words b .. nhw-1 of rows 32b .. 32b+31, contiguous in the blocked layout
+      if (lane == 0) {
+        for (int b = 0; b < nhw; ++b) {
+          const int slot = b % D;
+          if (b >= D) {                                                // every helper warp is done with block b - D
+            const uint32_t need = (uint32_t)(b - D + 1);
+            for (int h = 0; h < kScanHelpers; ++h)
+              while (ld_acquire_u32(&s_hprog[h]) < need) __nanosleep(64);
+            mbar_wait(&bar_full[slot], ((b - D) / D) & 1);             // its copy has landed (the chain skips that wait on dead blocks)
+          }
+          const uint32_t bytes = (uint32_t)((nhw - b) * 128);
+          mbar_expect_tx(&bar_full[slot], bytes);
+          tma_load_1d(ring + slot * slot_words, mgrp + ((long long)b * pitch32 + b) * 32, bytes, &bar_full[slot]);
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_issued)), "r"((uint32_t)(b + 1)) : "memory");
+        }
+      }
+    } else if (warp == 0) {
+      // ---- chain.  Per block: removed bits of its 32 rows (helpers: blocks <= b-4; own carries: blocks b-3..b-1) ->
+      //      32 greedy decisions, two per step -> keep word -> the kept rows' words b+1..b+3 OR-ed into three carries
+      //      (redux.or), so the helpers have four blocks of slack.  Groups of <= 2048 boxes read their words b..b+3
+      //      from the panel that was loaded once (no barrier probe per block: measured 36 cycles for the probe, 43 for
+      //      the issue-counter load, and neither overlaps the chain because both block the warp); larger groups take
+      //      them from the ring.
+      uint32_t c1 = 0, c2 = 0, c3 = 0;
+      uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;                         // words b .. b+3 of row 32 b + lane
+      bool have = false;                                               // d* hold block b's words
+      int slot = 0; uint32_t par = 0;                                  // b % D, (b / D) & 1 without a division per block
+      auto fetch = [&](int b, const uint32_t* blk, uint32_t& e0, uint32_t& e1, uint32_t& e2, uint32_t& e3) {
+        e0 = e1 = e2 = e3 = 0u;                                        // blk: word w of row `lane` at blk[(w - b) * 32]
+        if (lane < ng - 32 * b) {
+          e0 = blk[0];
+          if (b + 1 < nhw) e1 = blk[32];
+          if (b + 2 < nhw) e2 = blk[64];
+          if (b + 3 < nhw) e3 = blk[96];
+        }
+      };
+      if (use_panel) { fetch(0, panel + lane, d0, d1, d2, d3); have = true; }
+      for (int b = 0; b < nhw; ++b) {
+        if (b >= 4) {                                                  // every helper is done with the blocks <= b-4
+          const uint32_t need = (uint32_t)(b - 3);
+          while (!__all_sync(0xffffffffu, lane >= kScanHelpers || ld_acquire_u32(&s_hprog[lane & 7]) >= need)) {}
+        }
+        const int rows_b = min(32, ng - 32 * b);
+        uint32_t cur = ld_acquire_u32(&s_removed[b]) | c1;
+        if (rows_b < 32) cur |= ~0u << rows_b;
+        int slot_n = slot + 1; uint32_t par_n = par;
+        if (slot_n == D) { slot_n = 0; par_n ^= 1u; }
+        uint32_t keep = 0, n1 = 0, n2 = 0, n3 = 0;
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        bool have_n = false;
+        if (use_panel) {
+          if (b + 1 < nhw) { fetch(b + 1, panel + (b + 1) * 128 + lane, e0, e1, e2, e3); have_n = true; }
+        } else if (cur != ~0u) {
+          if (!have) {
+            // the barrier counts for THIS block only once the producer has armed it (blocks skipped as dead are not
+            // waited for, so the slot's previous phase may still be open)
+            while (ld_acquire_u32(&s_issued) <= (uint32_t)b) {}
+            mbar_wait(&bar_full[slot], par);
+            fetch(b, ring + slot * slot_words + lane, d0, d1, d2, d3);
+          }
+          if (b + 1 < nhw && ld_acquire_u32(&s_issued) > (uint32_t)(b + 1) && mbar_try_wait(&bar_full[slot_n], par_n)) {
+            fetch(b + 1, ring + slot_n * slot_words + lane, e0, e1, e2, e3);
+            have_n = true;
+          }
+        }
+        if (cur != ~0u) {                                              // a dead block needs neither its data nor a chain
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const uint32_t da = __shfl_sync(0xffffffffu, d0, k), db = __shfl_sync(0xffffffffu, d0, k + 1);
+            // two decisions from the same `cur`: row k is kept iff its bit is clear; row k+1 iff its bit is clear in
+            // cur and, when row k is kept, also in row k's diagonal word
+            const bool ka = !(cur & (1u << k));
+            const bool kb = ka ? !((cur | da) & (2u << k)) : !(cur & (2u << k));
+            cur |= (ka ? da : 0u) | (kb ? db : 0u);
+            keep |= (ka ? (1u << k) : 0u) | (kb ? (2u << k) : 0u);
+          }
+          const bool kept = (keep >> lane) & 1u;
+          n1 = __reduce_or_sync(0xffffffffu, kept ? d1 : 0u);
+          n2 = __reduce_or_sync(0xffffffffu, kept ? d2 : 0u);
+          n3 = __reduce_or_sync(0xffffffffu, kept ? d3 : 0u);
+        }
+        if (lane == 0) { s_keep[b] = keep; mbar_arrive(&bar_k[b % kScanSlotsMax]); }
+        c1 = c2 | n1;
+        c2 = c3 | n2;
+        c3 = n3;
+        d0 = e0; d1 = e1; d2 = e2; d3 = e3; have = have_n;
+        slot = slot_n; par = par_n;
+      }
+    } else {
+      // ---- helpers: warp hw owns the words w = hw + kScanHelpers * i; lane (i % 32) keeps the accumulator of its i-th
+      //      word in a register (two per lane cover nhw <= 256) and publishes it when the word's last block is done
+      const int hw = warp - 2;
+      uint32_t acc0 = 0, acc1 = 0;
+      for (int b = 0; b < nhw; ++b) {
+        mbar_wait(&bar_k[b % kScanSlotsMax], (b / kScanSlotsMax) & 1);
+        const uint32_t keep = ld_acquire_u32(&s_keep[b]);
+        if (keep && b + 4 < nhw) {
+          const int slot = b % D;
+          // the block's copy must have landed (in panel mode the chain never waits for the ring); the barrier counts for
+          // this block only once the producer has armed it
+          while (ld_acquire_u32(&s_issued) <= (uint32_t)b) {}
+          mbar_wait(&bar_full[slot], (b / D) & 1);
+          const uint32_t* blk = ring + slot * slot_words + lane - b * 32;
+          const bool kept = (keep >> lane) & 1u;
+          int i = (b + 4 - hw + kScanHelpers - 1) / kScanHelpers;      // first owned word >= b + 4
+          i = max(i, 0);
+          for (int w = hw + kScanHelpers * i; w < nhw; w += 4 * kScanHelpers, i += 4) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int wk = w + k * kScanHelpers; v[k] = (wk < nhw && kept) ? blk[wk * 32] : 0u; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t r = __reduce_or_sync(0xffffffffu, v[k]);
+              const int ik = i + k;
+              if (lane == (ik & 31)) { if (ik < 32) acc0 |= r; else acc1 |= r; }
+            }
+          }
+        }
+        // word b + 4 has now received every contribution the helpers owe it: publish it if this warp owns it
+        const int wf = b + 4;
+        if (wf < nhw && wf % kScanHelpers == hw) {
+          const int i = wf / kScanHelpers;
+          if (lane == (i & 31)) s_removed[wf] = (i < 32) ? acc0 : acc1;
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_hprog[hw])), "r"((uint32_t)(b + 1)) : "memory");
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < ng; i += kFusedThreads)
+      if ((s_keep[i >> 5] >> (i & 31)) & 1u) flags[order[start + i]] = 1;
+  }
+
+  stamp(5);
+  // ---------------------------------------------------------------- compaction by the CTA that finishes last
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int per = ((n + kFusedThreads - 1) / kFusedThreads + 15) & ~15;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  const uint4* f4 = reinterpret_cast<const uint4*>(flags);            // workspace slot is 128 B aligned and padded
+  int cnt = 0;
+  for (int i = lo; i < hi; i += 16) {
+    const uint4 v = __ldcg(f4 + (i >> 4));
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (i + k < hi) cnt += (wds[k >> 2] >> (8 * (k & 3))) & 1u;
+  }
+  int x = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) swarp[warp] = x;
+  __syncthreads();
+  int off = x - cnt;
+  for (int w = 0; w < warp; ++w) off += swarp[w];
+  for (int i = lo; i < hi; i += 16) {
+    const uint4 v = __ldcg(f4 + (i >> 4));
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (i + k < hi && ((wds[k >> 2] >> (8 * (k & 3))) & 1u)) keep_out[off++] = i + k;
+  }
+  if (tid == kFusedThreads - 1) { *n_keep = off; if (stamps) { stamps[6] = clock64(); stamps[7] = blockIdx.x; } }
+}
+
 // ------------------------------------------------------------------ host side
 struct NmsLayout {
   size_t keys_in, keys_out, idx_in, order, rows, cols, gbounds, prefix, flags, mask, cub, total;
@@ -548,10 +1023,12 @@ static NmsLayout nms_layout(int n, int n_groups, int fmt, size_t cub_bytes) {
   L.rows = take((size_t)n * rec); L.cols = take(fmt == 8 ? (size_t)n * rec : 0);
   L.gbounds = take((size_t)n_groups * 8); L.prefix = take((size_t)(n_groups + 3) * 4);
   L.flags = take((size_t)n + 16);
-  L.pitch32 = 2LL * ((n + 63) / 64);
-  L.mask = take((size_t)n * (size_t)L.pitch32 * 4);
+  L.pitch32 = 4LL * ((n + 127) / 128);                       // multiple of 4 words: rows are 16 B aligned (TMA bulk copies of the fused scan)
+  // the fused kernel stores every group's mask in 32-row blocks: up to 31 rows of padding per group
+  const size_t mask_rows = (size_t)n + ((n <= 8192 && n_groups <= 1024) ? 32 * (size_t)n_groups : 0);
+  L.mask = take(mask_rows * (size_t)L.pitch32 * 4);
   L.cub_bytes = cub_bytes; L.cub = take(cub_bytes);
-  L.total = off + 128;
+  L.total = off + 384;                                       // the last 256 bytes: phase stamps of the fused kernel (diagnostics)
   return L;
 }
 
@@ -560,6 +1037,26 @@ static int cub_temp_bytes(int n, int end_bit, size_t* bytes) {
   AIDET_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, *bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
                                              (const int*)nullptr, (int*)nullptr, n, 0, end_bit, (cudaStream_t)0));
   return AIDET_OK;
+}
+
+static bool coop_supported(int device) {
+  static int cached[64];                                    // 0 unknown, 1 yes, 2 no (benign race: same value)
+  if (device < 0 || device >= 64) return false;
+  if (!cached[device]) {
+    int v = 0;
+    cached[device] = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && v) ? 1 : 2;
+  }
+  return cached[device] == 1;
+}
+
+// resident CTAs per SM of the fused kernel with `smem` bytes of dynamic shared memory (0: does not fit)
+static int fused_occupancy(void* fn, size_t smem) {
+  if (smem > 200 * 1024) return 0;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kFusedThreads, smem) != cudaSuccess) return 0;
+  return occ;
 }
 
 template <class O>
@@ -577,6 +1074,39 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
   uint32_t* mask32 = (uint32_t*)(ws + L.mask);
 
   int* counters = prefix + n_groups + 1;                    // [0] tile ticket of the mask kernel, [1] finished scan CTAs
+  if (n <= kFusedMaxBoxes && n_groups <= kFusedMaxGroups && coop_supported(device)) {
+    // one cooperative launch: rank -> mask -> scan -> compaction (see nms_fused_kernel)
+    const int slot_max = 32 * ((n + 31) >> 5);               // ring slot if all n boxes fall into one group
+    // dynamic shared memory: all n keys (phase 1), later the scan's ring (+ the chain's panel for groups <= 2048 boxes,
+    // carved from its end).  Any group must get two ring slots; beyond that, problems of more than 2048 boxes stay at
+    // 48 KB (four CTAs per SM for the mask phase: per-image inputs hold many small groups, whose slots are tiny), smaller
+    // ones -- possibly ONE group -- take up to 72 KB so that the helpers' ring runs several blocks ahead
+    const int ring_words = (n > 32 * kPanelBlocks) ? max(2 * slot_max, 12288) : min(18432, 8 * slot_max + kPanelBlocks * 128);
+    const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12), (size_t)ring_words * 4);
+    void* fn = (cmp == AIDET_CMP_GE) ? (void*)nms_fused_kernel<O, true> : (void*)nms_fused_kernel<O, false>;
+    const int occ = fused_occupancy(fn, smem);
+    if (occ > 0) {
+      const int sms = sm_count(device);
+      const int grid = sms * min(occ, 4);
+      const int n_gwarps = grid * (kFusedThreads / 32);
+      // rows per mask unit: the finest split until there are >= 8 units per warp (estimated for evenly filled groups)
+      const int side = max(1, n / n_groups);
+      int rc_rows = 4;
+      while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= 8LL * n_gwarps) rc_rows <<= 1;
+      int nn = n, ng_ = n_groups, nthr = n_thr, rwords = ring_words;
+      long long pitch = L.pitch32;
+      int* done = counters + 1;
+      int* ticket = counters;
+      long long* stamps = prof_level() >= 2 ? (long long*)(ws + L.total - 256) : nullptr;   // phase stamps, see the kernel
+      void* args[] = {(void*)&boxes, (void*)&scores, (void*)&groups, &nn, &ng_, (void*)&thr, &nthr, &one, &rc_rows,
+                      &rows, &cols, &order, &flags, &gstart, &gend, &done, &ticket, &mask32, &pitch, &rwords, &keep_out, &n_keep,
+                      &stamps};
+      ProfScope prof(PROF_NMS_MASK, s);
+      AIDET_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kFusedThreads), args, smem, s));
+      count_launch(1);
+      return AIDET_OK;
+    }
+  }
   const bool small = n <= kRankSortMax && n_groups <= kRankMaxGroups;
   if (small) {
     const int warps = max(ceil_div(n, kRankBoxes), n_groups + 1);

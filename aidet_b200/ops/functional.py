@@ -222,13 +222,33 @@ def _scalar_thr(value, device):
     return t
 
 
-def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False, sync=True):
+_NMS_WS = {}
+
+
+def _nms_workspace(device, nbytes):
+    """Per-device scratch that grows on demand and is reused by every call on that device's current stream (the
+    reference cudaMallocs and frees its mask on every call, nms_kernel.cu:94,133).  Calls on the same stream are
+    ordered, so sharing is safe there; a caller that runs NMS on several streams at once passes its own `workspace`."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _NMS_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if len(_NMS_WS) > 64:
+            _NMS_WS.clear()
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _NMS_WS[key] = ws
+    return ws
+
+
+def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False, sync=True,
+                workspace=None):
     """Batched greedy NMS.  boxes (n,4|5|8), scores (n,), group_ids (n,) int or None.
 
     iou_thr: float, or a (n_groups,) tensor / sequence of per-group thresholds.
     Returns keep (k,) int64, ascending original index.  sync=False: no host read-back -- returns (keep (n,) whose first
     n_keep entries are valid, n_keep (1,) int32 device tensor); the call is then capturable in a CUDA graph (pass
     n_groups and a float / tensor threshold so that nothing else touches the host).
+    workspace: optional uint8 CUDA tensor of >= aidet_nms_workspace_bytes + 128 bytes owned by the caller; by default a
+    cached per-(device, stream) buffer is reused, so a call allocates nothing but its two result tensors.
     """
     fmt = boxes.size(-1)
     boxes = _f32c(boxes, fmt, "boxes")
@@ -266,7 +286,9 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
         ws_bytes = lib.aidet_nms_workspace_bytes(n, n_groups, fmt)
         if ws_bytes == 0:
             L.check(-2, "aidet_nms_workspace_bytes")
-        ws = torch.empty(ws_bytes + 128, dtype=torch.uint8, device=device)
+        ws = workspace if workspace is not None else _nms_workspace(device, ws_bytes + 128)
+        if ws.numel() < ws_bytes + 128 or ws.device != device or ws.dtype != torch.uint8:
+            raise ValueError("workspace must be a uint8 tensor of >= %d bytes on %s" % (ws_bytes + 128, device))
         base = ws.data_ptr()
         aligned = (base + 127) // 128 * 128
         L.check(lib.aidet_nms_batched_f32(L.dptr(boxes), fmt, L.dptr(scores), L.dptr(gids), n, L.dptr(thr),

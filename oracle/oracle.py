@@ -140,8 +140,10 @@ def nms_verify(boxes, scores, thr, keep, groups=None, cmp_ge=False, plus_one=Tru
     return int(bad), int(near.value)
 
 
-def roi_align_fwd(feat_nhwc, rois, scale, out_size, sample_num, variant, want_touched=False):
-    """feat (N,H,W,C) f32, rois (K,5|6) -> (K,ph,pw,C) f64 [, touched (N,H,W) bool]."""
+def roi_align_fwd(feat_nhwc, rois, scale, out_size, sample_num, variant, want_touched=False, unit_weights=False):
+    """feat (N,H,W,C) f32, rois (K,5|6) -> (K,ph,pw,C) f64 [, touched (N,H,W) bool].
+    unit_weights=True (error-bound mode for the tests): every accepted tap weighs 1 -> sum_taps x_t / count."""
+    lib().oracle_roi_set_unit_weights(C.c_int(int(unit_weights)))
     feat = np.ascontiguousarray(np.asarray(feat_nhwc, dtype=np.float32))
     N, H, W, Cc = feat.shape
     rois = np.asarray(rois, dtype=np.float32)
@@ -154,11 +156,13 @@ def roi_align_fwd(feat_nhwc, rois, scale, out_size, sample_num, variant, want_to
                                C.c_int(fmt), C.c_int(rois.shape[0]), C.c_double(scale), C.c_int(ph),
                                C.c_int(pw), C.c_int(sample_num), C.c_int(variant), _p(out),
                                _p(touched) if want_touched else None)
+    lib().oracle_roi_set_unit_weights(C.c_int(0))
     return (out, touched.astype(bool)) if want_touched else out
 
 
-def roi_align_bwd(grad_out, feat_shape_nhwc, rois, scale, sample_num, variant):
-    """grad_out (K,ph,pw,C) f32 -> grad_feat (N,H,W,C) f64."""
+def roi_align_bwd(grad_out, feat_shape_nhwc, rois, scale, sample_num, variant, unit_weights=False):
+    """grad_out (K,ph,pw,C) f32 -> grad_feat (N,H,W,C) f64.  unit_weights: see roi_align_fwd."""
+    lib().oracle_roi_set_unit_weights(C.c_int(int(unit_weights)))
     go = np.ascontiguousarray(np.asarray(grad_out, dtype=np.float32))
     K, ph, pw, Cc = go.shape
     N, H, W, C2 = feat_shape_nhwc
@@ -170,6 +174,7 @@ def roi_align_bwd(grad_out, feat_shape_nhwc, rois, scale, sample_num, variant):
     lib().oracle_roi_align_bwd(_p(go), C.c_int(N), C.c_int(H), C.c_int(W), C.c_int(Cc), _p(rois),
                                C.c_int(fmt), C.c_int(K), C.c_double(scale), C.c_int(ph), C.c_int(pw),
                                C.c_int(sample_num), C.c_int(variant), _p(gf))
+    lib().oracle_roi_set_unit_weights(C.c_int(0))
     return gf
 
 

@@ -67,6 +67,12 @@ static roi_geom decode_roi(const float* r, int roi_fmt, double scale, int varian
   return g;
 }
 
+/* Error-bound mode for the parity tests (NOT part of the restated algorithm): every accepted tap gets weight 1, so a
+ * forward over |features| (backward over |grad_out|) yields  sum_taps |x_t| / count  per element -- the quantity a
+ * float32 implementation's weight errors (a few ulp of the sample coordinates each) are multiplied by. */
+static int g_unit_weights = 0;
+void oracle_roi_set_unit_weights(int on) { g_unit_weights = on; }
+
 /* roi_align_kernel.cu:143-185: tap indices + weights; x_low = -1 marks a
  * rejected sample. */
 static void taps(int H, int W, double y, double x, double* w, int* yl, int* yh, int* xl, int* xh) {
@@ -80,6 +86,7 @@ static void taps(int H, int W, double y, double x, double* w, int* yl, int* yh, 
   if (*xl >= W - 1) { *xh = *xl = W - 1; x = (double)*xl; } else *xh = *xl + 1;
   double ly = y - *yl, lx = x - *xl, hy = 1. - ly, hx = 1. - lx;
   w[0] = hy * hx; w[1] = hy * lx; w[2] = ly * hx; w[3] = ly * lx;
+  if (g_unit_weights) w[0] = w[1] = w[2] = w[3] = 1.0;
 }
 
 static void sample_xy(const roi_geom* g, double bin_w, double bin_h, int ph_, int pw_, int iy, int ix,
