@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kFusedThreads, O::FMT == 8 ? 3 : 4)
 nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ groups,
                  int n, int n_groups, const float* __restrict__ thr, int n_thr, float one, int rc_rows,
                  typename O::Row* rows, typename O::Col* cols, int* order, uint8_t* flags, int* gstart, int* gend,
-                 int* done, int* ticket, uint32_t* mask32, long long pitch32, int ring_words,
+                 int* done, int* ticket, uint32_t* mask32, long long pitch32, int ring_words, int p1_ctas,
                  long long* __restrict__ keep_out, int* __restrict__ n_keep, long long* __restrict__ stamps) {
   using Row = typename O::Row; using Col = typename O::Col;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -649,23 +649,49 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     // before the first key is built (a plain loop exposes one L2 latency per iteration: 23 of them at config C2)
     uint64_t* skeys = reinterpret_cast<uint64_t*>(dyn);
     const int u_box = (n + kRankBoxes - 1) / kRankBoxes, u_all = u_box + n_groups + 1;
-    const int ctas_p1 = min((int)gridDim.x, (u_all + kWarps - 1) / kWarps);
+    // only the first wave of CTAs (one per SM: they start together and have the SM to themselves) takes part
+    const int ctas_p1 = min(p1_ctas, (u_all + kWarps - 1) / kWarps);
     if (blockIdx.x == 0 && tid == 0) { *done = 0; *ticket = 0; }
     if ((int)blockIdx.x < ctas_p1) {
-      for (int j0 = 0; j0 < n; j0 += 8 * kFusedThreads) {
-        float sc[8]; int gr[8];
+      auto put_key = [&](int j, float sc, int gr) {
+        const uint32_t g = min((uint32_t)gr, (uint32_t)n_groups);     // ids outside [0, n_groups): behind every group, never scanned
+        skeys[j] = ((uint64_t)g << kRankGroupShift) | ((uint64_t)(~orderable(sc)) << 13) | (uint64_t)j;
+      };
+      const bool vec = ((reinterpret_cast<uintptr_t>(scores) | reinterpret_cast<uintptr_t>(groups)) & 15) == 0;
+      if (vec) {
+        // four boxes per 128-bit load, four loads of each array in flight per thread: two round trips for n = 8192
+        const int nq = n >> 2;
+        for (int q0 = 0; q0 < nq; q0 += 4 * kFusedThreads) {
+          float4 sc[4]; int4 gr[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int j = j0 + k * kFusedThreads + tid;
-          sc[k] = (j < n) ? __ldg(scores + j) : 0.f;
-          gr[k] = (j < n && groups) ? __ldg(groups + j) : 0;
+          for (int k = 0; k < 4; ++k) {
+            const int qq = q0 + k * kFusedThreads + tid;
+            sc[k] = (qq < nq) ? __ldg(reinterpret_cast<const float4*>(scores) + qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gr[k] = (qq < nq && groups) ? __ldg(reinterpret_cast<const int4*>(groups) + qq) : make_int4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int qq = q0 + k * kFusedThreads + tid;
+            if (qq < nq) {
+              put_key(4 * qq, sc[k].x, gr[k].x); put_key(4 * qq + 1, sc[k].y, gr[k].y);
+              put_key(4 * qq + 2, sc[k].z, gr[k].z); put_key(4 * qq + 3, sc[k].w, gr[k].w);
+            }
+          }
         }
+        for (int j = 4 * nq + tid; j < n; j += kFusedThreads) put_key(j, __ldg(scores + j), groups ? __ldg(groups + j) : 0);
+      } else {
+        for (int j0 = 0; j0 < n; j0 += 8 * kFusedThreads) {
+          float sc[8]; int gr[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int j = j0 + k * kFusedThreads + tid;
-          if (j < n) {
-            const uint32_t g = min((uint32_t)gr[k], (uint32_t)n_groups);   // ids outside [0, n_groups): behind every group, never scanned
-            skeys[j] = ((uint64_t)g << kRankGroupShift) | ((uint64_t)(~orderable(sc[k])) << 13) | (uint64_t)j;
+          for (int k = 0; k < 8; ++k) {
+            const int j = j0 + k * kFusedThreads + tid;
+            sc[k] = (j < n) ? __ldg(scores + j) : 0.f;
+            gr[k] = (j < n && groups) ? __ldg(groups + j) : 0;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int j = j0 + k * kFusedThreads + tid;
+            if (j < n) put_key(j, sc[k], gr[k]);
           }
         }
       }
@@ -1093,13 +1119,13 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
       const int side = max(1, n / n_groups);
       int rc_rows = 4;
       while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= 8LL * n_gwarps) rc_rows <<= 1;
-      int nn = n, ng_ = n_groups, nthr = n_thr, rwords = ring_words;
+      int nn = n, ng_ = n_groups, nthr = n_thr, rwords = ring_words, p1 = min(grid, sms);
       long long pitch = L.pitch32;
       int* done = counters + 1;
       int* ticket = counters;
       long long* stamps = prof_level() >= 2 ? (long long*)(ws + L.total - 256) : nullptr;   // phase stamps, see the kernel
       void* args[] = {(void*)&boxes, (void*)&scores, (void*)&groups, &nn, &ng_, (void*)&thr, &nthr, &one, &rc_rows,
-                      &rows, &cols, &order, &flags, &gstart, &gend, &done, &ticket, &mask32, &pitch, &rwords, &keep_out, &n_keep,
+                      &rows, &cols, &order, &flags, &gstart, &gend, &done, &ticket, &mask32, &pitch, &rwords, &p1, &keep_out, &n_keep,
                       &stamps};
       ProfScope prof(PROF_NMS_MASK, s);
       AIDET_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kFusedThreads), args, smem, s));
