@@ -1100,6 +1100,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
   uint32_t* mask32 = (uint32_t*)(ws + L.mask);
 
   int* counters = prefix + n_groups + 1;                    // [0] tile ticket of the mask kernel, [1] finished scan CTAs
+  ProfScope prof(PROF_NMS_MASK, s);                          // device time of the WHOLE call (every kernel it enqueues)
   if (n <= kFusedMaxBoxes && n_groups <= kFusedMaxGroups && coop_supported(device)) {
     // one cooperative launch: rank -> mask -> scan -> compaction (see nms_fused_kernel)
     const int slot_max = 32 * ((n + 31) >> 5);               // ring slot if all n boxes fall into one group
@@ -1127,7 +1128,6 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
       void* args[] = {(void*)&boxes, (void*)&scores, (void*)&groups, &nn, &ng_, (void*)&thr, &nthr, &one, &rc_rows,
                       &rows, &cols, &order, &flags, &gstart, &gend, &done, &ticket, &mask32, &pitch, &rwords, &p1, &keep_out, &n_keep,
                       &stamps};
-      ProfScope prof(PROF_NMS_MASK, s);
       AIDET_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kFusedThreads), args, smem, s));
       count_launch(1);
       return AIDET_OK;
@@ -1162,7 +1162,6 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
   const int local_prefix = (small && n_groups <= kLocalGroups) ? 1 : 0;
   if (!local_prefix) nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix);
   {
-    ProfScope prof(PROF_NMS_MASK, s);
     // upper bound of the tile count: every group padded to full tiles
     long long max_tiles = (long long)(ceil_div(n, tile_rows) + n_groups) * (ceil_div(n, kTileCols) + 1);
     int grid = (int)min((long long)sms * 6, max(max_tiles, 1LL));

@@ -889,16 +889,28 @@ static int check_common(const int* H, const int* W, const float* scale, int n_le
 // bound); first merged version (r1b) 0.307 ms (merge prologue per bin row + 35 SASS instructions per entry); tap list
 // with branch-free per-count consumers 0.154 ms: 61.7 M warp instructions instead of 105.7 M, 57.6 M L1 sectors
 // instead of 98.2 M, now limited by load latency / DRAM efficiency of scattered 1 KB reads (profiles/r1e).
-// tuning / test switch (AIDET_ROI_FWD_UNMERGED=1): the per-sample forward (rroi_align_fast_kernel) instead of the tap-list kernel
-static const bool g_roi_fwd_unmerged = [] { const char* e = getenv("AIDET_ROI_FWD_UNMERGED"); return e && e[0] == '1'; }();
-
-// test switch (AIDET_ROI_BWD_UNMERGED=1): one tap per sample corner, no per-bin merge
-static const bool g_roi_bwd_unmerged = [] { const char* e = getenv("AIDET_ROI_BWD_UNMERGED"); return e && e[0] == '1'; }();
-static const int g_gather_px = [] { const char* e = getenv("AIDET_ROI_GATHER_PX"); int v = e ? atoi(e) : 8; return (v == 4 || v == 16) ? v : 8; }();   // pixels per gather warp (tuning)
-
-static const int g_tl_occ = [] { const char* e = getenv("AIDET_ROI_TL_OCC"); return e ? atoi(e) : 5; }();   // resident CTAs per SM the tap-list forward is compiled for (tuning)
-
-static const bool g_tl_pair = [] { const char* e = getenv("AIDET_ROI_TL_PAIR"); return !(e && e[0] == '0'); }();   // two channel chunks per warp when C % 256 == 0 (tuning switch: 0 = one)
+// Kernel-variant switches are COMPILE-TIME constants (the library keeps no environment-dependent state); a tuning build
+// overrides them with -D (scripts/build_variants.sh).  Defaults = the variants measured fastest on config C3.
+#ifndef AIDET_ROI_FWD_UNMERGED
+#define AIDET_ROI_FWD_UNMERGED 0      // 1: per-sample forward (rroi_align_fast_kernel) instead of the tap-list kernel
+#endif
+#ifndef AIDET_ROI_BWD_UNMERGED
+#define AIDET_ROI_BWD_UNMERGED 0      // 1: one tap per sample corner in the gather backward, no per-bin merge
+#endif
+#ifndef AIDET_ROI_GATHER_PX
+#define AIDET_ROI_GATHER_PX 8         // pixels per gather warp: 4, 8 or 16
+#endif
+#ifndef AIDET_ROI_TL_OCC
+#define AIDET_ROI_TL_OCC 5            // resident CTAs per SM of the one-chunk tap-list forward: 4, 5 or 6
+#endif
+#ifndef AIDET_ROI_TL_PAIR
+#define AIDET_ROI_TL_PAIR 1           // two channel chunks per warp when C % 256 == 0
+#endif
+constexpr bool g_roi_fwd_unmerged = AIDET_ROI_FWD_UNMERGED != 0;
+constexpr bool g_roi_bwd_unmerged = AIDET_ROI_BWD_UNMERGED != 0;
+constexpr int g_gather_px = (AIDET_ROI_GATHER_PX == 4 || AIDET_ROI_GATHER_PX == 16) ? AIDET_ROI_GATHER_PX : 8;
+constexpr int g_tl_occ = AIDET_ROI_TL_OCC;
+constexpr bool g_tl_pair = AIDET_ROI_TL_PAIR != 0;
 
 static int lanes_for(int nch) { int cl = 1; while (cl < nch && cl < 256) cl <<= 1; return cl; }
 

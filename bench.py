@@ -221,6 +221,15 @@ def wall_timed(D, dev, steps, warmup, fn):
 
 
 # ------------------------------------------------------------------ workloads
+def iou_config(n, G):
+    """`config` of the headline line; the reference arm prints the identical dict (same workload, same keys)."""
+    rows_per = (n + G - 1) // G
+    return {"workload": "C4 rotated IoU matrix %dx%d theta-OBB (cx,cy,w,h,theta), dense synthetic set, rows sharded over "
+                        "the GPUs + all-gather of the shard results when there are several" % (n, n),
+            "iou_n": n, "box_format": "thetaobb (n,5)",
+            "l2": "result %.1f GB per step >> 126 MB L2 (no flush needed); small legs flush L2 between steps" % (n * float(n) * 4 / 1e9)}
+
+
 def iou_inputs(n, dense=True):
     from aidet_b200 import synth
     a, _ = synth.dota_boxes(n, side=16384, seed=4, dense=dense)
@@ -355,17 +364,25 @@ def run_ours(args, D):
                 probe = torch.arange(0, n, max(1, n // 64), device=dev)
                 same = bool(torch.equal(sym.tensor[:n][probe], out[:n][probe]))
                 same = D.max_float(0.0 if same else 1.0, dev) == 0.0
+                # ... and the float64 oracle on 64 rows per rank, drawn from ALL shards (checker only: 64 x n pairs on the host)
+                import numpy as np
+                from oracle import oracle as O
+                rs_ = np.sort(np.random.default_rng(100 + r).choice(n, 64, replace=False))
+                got_ = sym.tensor[:n][torch.from_numpy(rs_).to(dev)].cpu().numpy().astype(np.float64)
+                err_ = float(np.abs(got_ - O.riou_matrix(a.numpy()[rs_], b.numpy())).max())
+                err_ = D.max_float(err_, dev)
                 bytes_out = float(rows_per) * n * 4 * (G - 1)            # leaves this GPU over NVLink per step
                 multi["fused_peer_stores"] = {
                     "value": pairs / fms_step / 1e6, "unit": "Gpairs/s", "ms_per_step": fms_step,
                     "kernel_ms": D.max_float(fk_ms / max(fk_cnt, 1), dev), "matches_nccl_path": same,
+                    "max_abs_err": err_, "max_abs_err_how": "64 rows per rank (all shards) of the gathered matrix vs the float64 oracle; bound 1e-5",
                     "nvlink_bytes_out_per_rank": bytes_out, "nvlink_out_gbs": bytes_out / (fms_step * 1e-3) / 1e9,
                     "link_roofline": {"bound": "nvlink", "peak": 770.0, "unit": "GB/s per direction per GPU (measured peer copy, "
                                       "B200_PROFILING.md)", "frac": bytes_out / (fms_step * 1e-3) / 1e9 / 770.0,
                                       "target_ms": max(comp_ms, bytes_out / 770e9 * 1e3)},
                     "how": "aidet_riou_matrix_multi_f32: each tile is stored to the same rows of every rank's symmetric-memory "
                            "buffer from inside the kernel (NVLink peer stores), two symmetric-memory barriers, no NCCL on the data path"}
-                if same and fms_step < ms_step:
+                if same and err_ <= 1e-5 and fms_step < ms_step:
                     ms_step, launches, k_ms_avg = fms_step, flaunches, D.max_float(fk_ms / max(fk_cnt, 1), dev)
                 # NVSwitch multicast form: one multimem.st per element, replicated by the switch (NVLS)
                 has_mc = D.max_float(0.0 if sym.mc_ptr else 1.0, dev) == 0.0
@@ -404,11 +421,7 @@ def run_ours(args, D):
             "metric": "rotated IoU Gpairs/s", "value": pairs / ms_step / 1e6, "unit": "Gpairs/s",
             "n_gpus": G, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4 rotated IoU matrix %dx%d theta-OBB (cx,cy,w,h,theta), dense synthetic set, "
-                                   "rows sharded over %d GPU(s)%s" % (n, n, G, " + all-gather of the shard results (fused NVLink peer "
-                                                                           "stores or NCCL, see multi_gpu)" if D.on else ""),
-                       "rows_per_rank": rows_per, "l2": "output %.1f GB per step >> 126 MB L2 (no flush needed)"
-                                                        % (rows_per * n * 4 / 1e9)},
+            "config": dict(iou_config(n, G), rows_per_rank=rows_per, n_gpus=G),
             "compute_only": {"value": pairs / comp_ms / 1e6, "unit": "Gpairs/s", "ms_per_step": comp_ms},
             "multi_gpu": multi,
             "gpu_launches": int(launches),
@@ -433,6 +446,26 @@ def run_ours(args, D):
         sm_, _ = timed(D, dev, args.steps, args.warmup, lambda: Fn.riou_matrix(sa[r * rs:(r + 1) * rs], sb, out=so))
         line["dota_shaped"] = {"value": float(ns) * ns / (sm_ / args.steps) / 1e6, "unit": "Gpairs/s",
                                "workload": "%dx%d DOTA-shaped (clustered, sparse) boxes, compute only" % (ns, ns)}
+
+        # 8-point (point-OBB) inputs of the same dense set, 32768 x 32768: rectangles given by their corners (what
+        # thetaobb2pointobb / hobb2pointobb / the DOTA txt rows hold) and free convex quads (corners jittered by 3 % of
+        # the box size: what a point-OBB head regresses), same 256 flop/pair charge
+        q8 = {}
+        da8, db8 = iou_inputs(ns, dense=True)
+        sets8 = (("rect_as_8pt", synth.thetaobb2pointobb(da8).float(), synth.thetaobb2pointobb(db8).float()),
+                 ("free_quads", synth.free_quads(da8, rel_noise=0.03, seed=7)[0].float(),
+                  synth.free_quads(db8, rel_noise=0.03, seed=8)[0].float()))
+        for tag8, qa, qb in sets8:
+            qa, qb = qa.to(dev), qb.to(dev)
+            L.prof_read(L.PROF_RIOU, reset=True)
+            qm, _ = timed(D, dev, args.steps, args.warmup, lambda: Fn.riou_matrix(qa[r * rs:(r + 1) * rs], qb, out=so))
+            qk, qc = L.prof_read(L.PROF_RIOU, reset=True)
+            qk_avg = D.max_float(qk / max(qc, 1), dev)
+            q_ach = float(rs) * ns * F_PAIR / (qk_avg * 1e-3) / 1e12
+            q8[tag8] = {"value": float(ns) * ns / (qm / args.steps) / 1e6, "unit": "Gpairs/s", "kernel_ms": qk_avg,
+                        "roofline_frac": q_ach / FP32_PEAK_NOMINAL}
+        q8["workload"] = "%dx%d dense set as 8-point boxes, compute only, rows sharded over the GPUs" % (ns, ns)
+        line["iou_8point"] = q8
 
         if not args.no_e2e:
             # e2e: boxes in pinned host memory -> H2D -> kernel -> D2H of the result, streamed in row
@@ -479,8 +512,11 @@ def run_ours(args, D):
     # ---------------- batched rotated NMS (C2)
     if args.workload in ("all", "nms"):
         nms = {}
-        for tag, dense, images in (("c2", False, 1), ("c2_dense", True, 1), ("c2x8_dense", True, 8)):
+        for tag, dense, images, fmt8 in (("c2", False, 1, False), ("c2_dense", True, 1, False), ("c2x8_dense", True, 8, False),
+                                         ("c2_8point", False, 1, True), ("c2_dense_8point", True, 1, True)):
             cb, cs, cg, ng = nms_inputs(dense=dense, images=images)
+            if fmt8:
+                cb = synth.thetaobb2pointobb(cb).float()
             # shard groups over ranks (independent units, no data-path collective)
             mine = (cg % G) == r if G > 1 else torch.ones_like(cg, dtype=torch.bool)
             cbd, csd, cgd = cb[mine].to(dev), cs[mine].to(dev), cg[mine].to(dev)
@@ -495,25 +531,29 @@ def run_ours(args, D):
             nms[tag] = {"value": nb / (ms / args.steps) / 1e3, "unit": "Mboxes/s", "ms_per_step": ms / args.steps,
                         "boxes": int(nb), "groups": ng, "gpu_launches": int(launches),
                         "roofline": {"bound": "fp32-alu", "achieved": ach, "peak": FP32_PEAK_NOMINAL,
-                                     "unit": "TFLOP/s", "frac": ach / FP32_PEAK_NOMINAL, "kernel": "nms_mask_kernel<NmsRect>",
+                                     "unit": "TFLOP/s", "frac": ach / FP32_PEAK_NOMINAL,
+                                     "kernel": "whole call on the device (fused rank+mask+scan+compact kernel for n <= 8192; "
+                                               "sort + mask + scan kernels above)",
                                      "kernel_ms": k_avg, "charged_pairs_per_launch": gp, "traffic": None}}
-        # roofline config: ONE group of 16384 dense boxes (134 M pairs) -- the C2 groups (~390 boxes) are launch bound
-        bb, bs_ = synth.dota_boxes(16384, side=16384, seed=11, dense=True)
-        if G > 1:
-            bb, bs_ = bb[r::G].contiguous(), bs_[r::G].contiguous()
-        bbd, bsd = bb.to(dev), bs_.to(dev)
-        L.prof_read(L.PROF_NMS_MASK, reset=True)
-        ms, launches = timed(D, dev, args.steps, args.warmup, lambda: Fn.nms_batched(bbd, bsd, None, 0.5), flush=flush)
-        k_ms, k_cnt = L.prof_read(L.PROF_NMS_MASK, reset=True)
-        k_avg = D.max_float(k_ms / max(k_cnt, 1), dev)
-        gp = bbd.shape[0] * (bbd.shape[0] - 1) / 2.0
-        ach = gp * F_PAIR / (k_avg * 1e-3) / 1e12
-        nms["one_group_dense"] = {"value": D.sum_float(float(bbd.shape[0]), dev) / (ms / args.steps) / 1e3, "unit": "Mboxes/s",
-                                  "ms_per_step": ms / args.steps, "boxes": int(bbd.shape[0]), "groups": 1,
-                                  "gpu_launches": int(launches),
-                                  "roofline": {"bound": "fp32-alu", "achieved": ach, "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s",
-                                               "frac": ach / FP32_PEAK_NOMINAL, "kernel": "nms_mask_kernel<NmsRect>",
-                                               "kernel_ms": k_avg, "charged_pairs_per_launch": gp, "traffic": None}}
+        # roofline config: ONE group of 16384 dense boxes (134 M pairs).  A single group does not shard (the greedy scan
+        # is sequential in score order): at N > 1 every rank runs the same group -- replicas only, the figure is per replica
+        for tag, fmt8 in (("one_group_dense", False), ("one_group_dense_8point", True)):
+            bb, bs_ = synth.dota_boxes(16384, side=16384, seed=11, dense=True)
+            if fmt8:
+                bb = synth.thetaobb2pointobb(bb).float()
+            bbd, bsd = bb.to(dev), bs_.to(dev)
+            L.prof_read(L.PROF_NMS_MASK, reset=True)
+            ms, launches = timed(D, dev, args.steps, args.warmup, lambda: Fn.nms_batched(bbd, bsd, None, 0.5), flush=flush)
+            k_ms, k_cnt = L.prof_read(L.PROF_NMS_MASK, reset=True)
+            k_avg = D.max_float(k_ms / max(k_cnt, 1), dev)
+            gp = bbd.shape[0] * (bbd.shape[0] - 1) / 2.0
+            ach = gp * F_PAIR / (k_avg * 1e-3) / 1e12
+            nms[tag] = {"value": float(bbd.shape[0]) / (ms / args.steps) / 1e3, "unit": "Mboxes/s",
+                        "ms_per_step": ms / args.steps, "boxes": int(bbd.shape[0]), "groups": 1,
+                        "gpu_launches": int(launches), "scaling": "replicas only (per replica)",
+                        "roofline": {"bound": "fp32-alu", "achieved": ach, "peak": FP32_PEAK_NOMINAL, "unit": "TFLOP/s",
+                                     "frac": ach / FP32_PEAK_NOMINAL, "kernel": "whole call on the device (sort + mask + scan + compact)",
+                                     "kernel_ms": k_avg, "charged_pairs_per_launch": gp, "traffic": None}}
         # config C5: 4000^2 scene, 25 tiles (1024, overlap 200), per-tile NMS + cross-tile class-wise merge; tiles and
         # merge classes sharded over the ranks, survivors exchanged with two small all-gathers
         from aidet_b200 import sharded
@@ -529,7 +569,8 @@ def run_ours(args, D):
                                        "NMS @0.5 + cross-tile merge with the class thresholds of dota.py:324"}
         nms["workload"] = ("C2: 2000 proposals x 15 classes, score>0.05 candidates, thr 0.5, one launch over all "
                            "classes (c2 = DOTA-shaped, c2_dense = every pair intersects, c2x8 = 8 tiles batched); "
-                           "L2 flushed between steps; time = sort+gather+mask+scan+compact+count readback")
+                           "*_8point = the same boxes as corner lists; L2 flushed between steps; ms_per_step = whole call incl. the "
+                           "count read-back, roofline.kernel_ms = all kernels of the call on the device")
         if G == 1:
             # Soft-NMS (nms_cpu.cpp:70-201 is the reference's only implementation): all 15 classes in one launch
             sd, sg, sng = soft_nms_inputs()
@@ -631,7 +672,13 @@ def run_ours(args, D):
                                         if "rroi_gather_kernel_bwd" in TRAFFIC else None),
                             "traffic_source": "ncu dram read+write of the fwd kernel + the gather-backward kernel, one C3 launch each (%s)" % TRAFFIC.get("source"),
                             "fwd_frac": bytes_fwd / (fms * 1e-3) / 1e9 / hbm_peak,
-                            "bwd_frac": bytes_bwd / (bms * 1e-3) / 1e9 / hbm_peak}}
+                            "bwd_frac": bytes_bwd / (bms * 1e-3) / 1e9 / hbm_peak,
+                            # the same with the bytes the kernels really move (ncu DRAM read + write of the committed capture):
+                            # the gather backward never writes the zero-fill the algorithmic formula charges
+                            "fwd_frac_dram": (TRAFFIC["rroi_align_fwd_taplist_kernel"]["bytes"] / (fms * 1e-3) / 1e9 / hbm_peak
+                                              if "rroi_align_fwd_taplist_kernel" in TRAFFIC else None),
+                            "bwd_frac_dram": (TRAFFIC["rroi_gather_kernel_bwd"]["bytes"] / (bms * 1e-3) / 1e9 / hbm_peak
+                                              if "rroi_gather_kernel_bwd" in TRAFFIC else None)}}
         if not args.no_e2e:
             fh = [f.pin_memory() for f in feats_h]
             rh, lh = rois_h.pin_memory(), lvl_h.pin_memory()
@@ -760,6 +807,33 @@ def run_ours(args, D):
                    "workload": "C2: batched rotated NMS of the 15 classes (3 kernels), keep count left on the device"},
             "how": "CUDA events around %d back-to-back calls; graph = one torch.cuda.CUDAGraph replayed as often" % (5 if args.quick else 200)}
 
+    # the driver's record keeps the standard keys only: the other two quantities of the metric (NMS Mboxes/s, RoIAlign
+    # GB/s) and the exchange-free IoU figure ride along inside `roofline`, which it keeps whole
+    if "roofline" in line:
+        ops = {}
+        if "compute_only" in line:
+            ops["iou_compute_only_gpairs_s"] = line["compute_only"]["value"]
+        if "iou_8point" in line:
+            ops["iou_8point_rect_gpairs_s"] = line["iou_8point"]["rect_as_8pt"]["value"]
+            ops["iou_8point_rect_frac"] = line["iou_8point"]["rect_as_8pt"]["roofline_frac"]
+            ops["iou_8point_free_quads_gpairs_s"] = line["iou_8point"]["free_quads"]["value"]
+            ops["iou_8point_free_quads_frac"] = line["iou_8point"]["free_quads"]["roofline_frac"]
+        if "nms" in line:
+            for k in ("c2", "c2_dense", "c2x8_dense", "one_group_dense", "c2_8point", "one_group_dense_8point"):
+                if k in line["nms"]:
+                    ops["nms_%s_mboxes_s" % k] = line["nms"][k]["value"]
+                    ops["nms_%s_whole_call_frac" % k] = line["nms"][k]["roofline"]["frac"]
+        if "latency" in line:
+            ops["c1_graph_us"] = line["latency"]["c1"]["graph_us"]
+            ops["c2_graph_us"] = line["latency"]["c2"]["graph_us"]
+        if "roialign" in line:
+            ops["roialign_gbs"] = line["roialign"]["value"]
+            ops["roialign_frac"] = line["roialign"]["roofline"]["frac"]
+            ops["roialign_fwd_ms"] = line["roialign"]["fwd"]["ms"]
+            ops["roialign_bwd_ms"] = line["roialign"]["bwd"]["ms"]
+            ops["roialign_fwd_frac"] = line["roialign"]["roofline"]["fwd_frac"]
+            ops["roialign_bwd_frac_dram"] = line["roialign"]["roofline"]["bwd_frac_dram"]
+        line["roofline"]["other_ops"] = ops
     line["clocks"] = sampler.stop() if sampler else None
     line["ffma_peak_tflops_measured"] = ffma
     return line, dev
@@ -873,6 +947,33 @@ def cpu_roi(sample_rois=512):
     return by / dt / 1e9, dt
 
 
+def cpu_roi_torchvision():
+    """torchvision.ops.roi_align on the CPU (the implementation the reference itself offers,
+    mmdet/ops/roi_align/roi_align.py:138-141) forward + autograd backward on ALL 4096 C3 RoIs, level by level as
+    SingleRoIExtractor loops (single_level.py:96-107).  torchvision has no rotated RoIAlign: the RoIs are the C3 RoIs
+    with theta = 0 (same centres and sizes, hence the same amount of sampling and of touched pixels)."""
+    import torch
+    import torchvision
+    from aidet_b200 import synth
+    feats = [f.permute(0, 3, 1, 2) for f in synth.fpn_features()]          # NCHW views of the NHWC maps (channels_last)
+    rois, lvl = synth.rotated_rois()
+    hbb = torch.cat([rois[:, :1], rois[:, 1:3] - rois[:, 3:5] / 2, rois[:, 1:3] + rois[:, 3:5] / 2], 1)
+    C = feats[0].shape[1]
+    xs = [f.clone().requires_grad_(True) for f in feats]
+    t0 = time.perf_counter()
+    outs = []
+    for l, sc in enumerate(SCALES):
+        sel = lvl == l
+        if sel.any():
+            outs.append(torchvision.ops.roi_align(xs[l], hbb[sel], (7, 7), sc, 2, aligned=True))
+    torch.cat(outs).sum().backward()
+    dt = time.perf_counter() - t0
+    touched = roi_touched_bytes(torch.cat([rois[:, :5], torch.zeros(rois.shape[0], 1)], 1), lvl, feats[0].shape[0], C, device="cpu")
+    K = rois.shape[0]
+    by = 4.0 * (C * touched + K * 49 * C + 6 * K) * 2 + 4.0 * sum(f.numel() for f in feats)
+    return by / dt / 1e9, dt, torch.get_num_threads()
+
+
 def cpu_baselines(args):
     cores = os.cpu_count()
     out = {}
@@ -898,6 +999,14 @@ def cpu_baselines(args):
         v, dt = cpu_roi(512)
         out["roialign"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": "port",
                            "sample": "first 512 of the 4096 C3 RoIs, fwd+bwd, float64 oracle (oracle/oracle_roi.c), OpenMP, %.1f s" % dt}
+        try:
+            tv, tdt, tthreads = cpu_roi_torchvision()
+            out["roialign_torchvision"] = {"value": tv, "unit": "GB/s", "cores": tthreads, "kind": "reference",
+                                           "sample": "torchvision.ops.roi_align CPU forward + autograd backward, float32, all 4096 C3 "
+                                                     "RoIs at theta = 0, per level (the CPU implementation the reference endorses, "
+                                                     "roi_align.py:138-141), %.1f s" % tdt}
+        except Exception as exc:                     # torchvision missing / too old on the box: the port figure stands
+            out["roialign_torchvision"] = {"unavailable": repr(exc)[:200]}
     return out
 
 
@@ -924,11 +1033,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "rotated IoU Gpairs/s", "value": value, "unit": "Gpairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 rotated IoU matrix %dx%d theta-OBB, dense synthetic set; each step = a %dx%d "
-                                   "block of it on the host CPU" % (n, n, sample, sample)},
+            "config": dict(iou_config(n, args.gpus), rows_per_rank=(n + args.gpus - 1) // args.gpus, n_gpus=args.gpus),
             "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": cores, "kind": "port",
-                             "sample": "%dx%d block per step, float64 oracle port (the reference has no in-tree rotated "
-                                       "IoU; wwtool/polyiou is un-vendored), OpenMP over all cores" % (sample, sample)},
+                             "sample": "each step = a %dx%d block of the config's %dx%d matrix (a rate, so the block size does not "
+                                       "enter), float64 oracle port (the reference has no in-tree rotated IoU; wwtool/polyiou is "
+                                       "un-vendored), OpenMP over all cores" % (sample, sample, n, n)},
             "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if args.workload in ("all", "nms"):
@@ -970,13 +1079,15 @@ def main():
         if "iou" in cb:
             line["cpu_baseline"] = cb.pop("iou")
         for k, v in cb.items():
-            tgt = {"nms": "nms", "nms_hbb_reference": "nms", "soft_nms_reference": "nms", "roialign": "roialign"}[k]
+            tgt = {"nms": "nms", "nms_hbb_reference": "nms", "soft_nms_reference": "nms", "roialign": "roialign",
+                   "roialign_torchvision": "roialign"}[k]
             if tgt in line:
                 if k == "soft_nms_reference":
                     if "soft_nms" in line[tgt]:
                         line[tgt]["soft_nms"]["cpu_baseline"] = v
                     continue
-                line[tgt]["cpu_baseline" if k != "nms_hbb_reference" else "cpu_baseline_hbb_reference"] = v
+                line[tgt][{"nms_hbb_reference": "cpu_baseline_hbb_reference",
+                           "roialign_torchvision": "cpu_baseline_torchvision"}.get(k, "cpu_baseline")] = v
     if D.rank == 0:
         emit(line)
     D.finish()

@@ -41,12 +41,13 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 const char* aidet_last_error(void);
 int aidet_version(void);                       /* 100 * major + minor */
-/* Device-side timing of the dominant kernel of each op (CUDA events recorded on
- * the caller's stream around that kernel only).  enable != 0 starts collecting. */
+/* Diagnostics (process-wide switch and counters, off by default; the only state of the library besides the
+ * thread-local error string).  enable 1: device-side timing of each op (CUDA events recorded on the caller's stream);
+ * enable 2: the fused NMS kernel additionally leaves its phase time stamps in the last 256 bytes of its workspace. */
 int aidet_prof_enable(int enable);
-/* kind: 0 = riou matrix kernel, 1 = rnms mask kernel, 2 = rroi fwd kernel,
- * 3 = rroi bwd kernel.  Synchronises the recorded events, returns accumulated
- * milliseconds and launch count since the last reset. */
+/* kind: 0 = riou matrix kernel, 1 = batched NMS, the WHOLE call (every kernel it enqueues: the roofline of
+ * SURVEY 8d charges the call), 2 = rroi fwd kernel, 3 = rroi bwd (all kernels of the gather form).
+ * Synchronises the recorded events, returns accumulated milliseconds and call count since the last reset. */
 int aidet_prof_read(int kind, double* ms_total, long long* launches, int reset);
 /* Total number of kernel launches issued by this library since load (all ops). */
 long long aidet_launch_count(void);
