@@ -62,7 +62,8 @@ using RectCol = Rect;
 struct AIDET_ALIGN16 QuadRow {
   float x[4], y[4];              // CCW corner offsets about the centroid (mx,my)
   float area, rad, mx, my;       // |area|, bounding radius about (mx,my)
-  float pad[4];
+  float ux, uy, vx, vy;          // parallelograms (rectangles given by their corners): half edge vectors, corners =
+                                 // centre -+ u -+ v; ux = NaN otherwise (see quad_is_para / para_inter)
 };
 struct AIDET_ALIGN16 QuadCol {
   float ox, oy;                  // b0
@@ -308,7 +309,73 @@ AIDET_HD float quad_tri_inter(const QuadRow& a, float ox, float oy, float e1x, f
   return aD * s;
 }
 
+
+// ------------------------------------- parallelogram ^ parallelogram (8-point boxes that are rectangles)
+//
+// Most 8-point boxes ARE rectangles (thetaobb2pointobb / hobb2pointobb output, the DOTA txt rows, mmdet/core/rbbox/
+// transforms.py:45-55,137-163).  For two parallelograms the fan of two triangles (8 triangle-edge integrals with three
+// reciprocals each, ~550 instructions) is not needed: the affine map that takes B to the square [-1,1]^2 keeps A a
+// parallelogram, so area(A ^ B) = |det M_B| * area(A' ^ square) and A' ^ square is the rectangle integral of rect_inter
+// with one pair of reciprocals per edge DIRECTION (four in all) instead of the rotation's two.
+// A box takes this path when its corners satisfy p0 + p2 == p1 + p3 up to a few float32 ulps of the coordinates; the
+// parallelogram used is the least-squares one (each corner moves by a quarter of that residual).
+
+// residual |p0 + p2 - p1 - p3| (L1) against a few float32 ulps of the coordinate magnitude (what rounding the corners of
+// an exact rectangle leaves) AND against the box size (the overlap moves by ~0.15 residual / size: 4e-5 keeps it under
+// 6e-6 -- boxes whose coordinates are so large that rounding alone exceeds this go through the general path)
+AIDET_HD float para_tolerance(float mx, float my, float rad) {
+  return fminf(4.8e-7f * (fabsf(mx) + fabsf(my) + rad), 4e-5f * rad);
+}
+AIDET_HD bool quad_is_para(const float* x, const float* y, float mx, float my, float rad) {
+  const float res = fabsf((x[0] + x[2]) - (x[1] + x[3])) + fabsf((y[0] + y[2]) - (y[1] + y[3]));
+  return res <= para_tolerance(mx, my, rad);
+}
+
+// Edge integral of rect_edge for the edge p + t d, t in [0, 1], against the square |x|,|y| <= 1 shifted by xref in x;
+// rdx, rdy = 1/d.x, 1/d.y (never 0 / inf: the caller adds 1e-20 to the components).
+AIDET_HD float para_edge(float px, float py, float dx, float rdx, float rdy, float xref) {
+  const float ardx = fabsf(rdx), sx = copysignf(1.0f, dx);
+  const float xo = -xref * rdx;
+  return rect_edge(px, -py * rdy, fabsf(rdy), 1.0f, -px * rdx, xo - ardx, xo + ardx, -xref - sx, -xref + sx, 0.5f * dx);
+}
+
+// a, b: both parallelograms (a.ux is not NaN; the caller checked b with quad_col_is_para).  Intersection area.
+AIDET_HD float para_inter(const QuadRow& a, const QuadCol& b) {
+  // B: centre (mx, my), half edges uB = (e1 + e2 - e3) / 4, vB = (e3 + e2 - e1) / 4 (least squares over the four corners)
+  const float ubx = 0.25f * (b.e1x + b.e2x - b.e3x), uby = 0.25f * (b.e1y + b.e2y - b.e3y);
+  const float vbx = 0.25f * (b.e3x + b.e2x - b.e1x), vby = 0.25f * (b.e3y + b.e2y - b.e1y);
+  const float det = ubx * vby - uby * vbx;                    // > 0 (CCW); 0 only for degenerate boxes (area 0 -> overlap 0)
+  const float rdet = frcp(det + 1e-30f);
+  // M^-1 = [vby -vbx; -uby ubx] / det: A's centre and half edges in B's frame (B = [-1,1]^2)
+  // centres: the exact mean of the four corners on both sides -- (a.mx, a.my) is that mean ROUNDED (the corner offsets
+  // carry the remainder), B's corners are o, o + e1, o + e2, o + e3
+  const float relx = (a.mx - b.ox) + (0.25f * ((a.x[0] + a.x[2]) + (a.x[1] + a.x[3])) - 0.25f * (b.e1x + b.e2x + b.e3x));
+  const float rely = (a.my - b.oy) + (0.25f * ((a.y[0] + a.y[2]) + (a.y[1] + a.y[3])) - 0.25f * (b.e1y + b.e2y + b.e3y));
+  float rx = (vby * relx - vbx * rely) * rdet;
+  const float ry = (ubx * rely - uby * relx) * rdet;
+  const float ux = (vby * a.ux - vbx * a.uy) * rdet + 1e-20f, uy = (ubx * a.uy - uby * a.ux) * rdet + 1e-20f;
+  const float vx = (vby * a.vx - vbx * a.vy) * rdet + 1e-20f, vy = (ubx * a.vy - uby * a.vx) * rdet + 1e-20f;
+  const float xref = fminf(fmaxf(rx, -1.0f), 1.0f);           // same shift as rect_inter: terms of the order of the smaller box
+  rx -= xref;
+  const float mx = rx - ux, my = ry - uy;
+  const float p0x = mx - vx, p0y = my - vy;                    // corners p0 = r-u-v, p1 = r+u-v, p3 = r-u+v (CCW)
+  const float p3x = mx + vx, p3y = my + vy;
+  const float dux = ux + ux, duy = uy + uy, dvx = vx + vx, dvy = vy + vy;
+  const float p1x = p0x + dux, p1y = p0y + duy;
+  const float rux = frcp(dux), ruy = frcp(duy), rvx = frcp(dvx), rvy = frcp(dvy);
+  // edges p0->p1 (+du), p1->p2 (+dv), p2->p3 == -(p3->p2, +du), p3->p0 == -(p0->p3, +dv)
+  const float iu = para_edge(p0x, p0y, dux, rux, ruy, xref) - para_edge(p3x, p3y, dux, rux, ruy, xref);
+  const float iv = para_edge(p1x, p1y, dvx, rvx, rvy, xref) - para_edge(p0x, p0y, dvx, rvx, rvy, xref);
+  return det * fmaf(duy, iu, dvy * iv);
+}
+
+AIDET_HD bool quad_col_is_para(const QuadCol& b) {
+  const float res = fabsf(b.e2x - b.e1x - b.e3x) + fabsf(b.e2y - b.e1y - b.e3y);
+  return res <= para_tolerance(b.mx, b.my, b.rad);
+}
+
 AIDET_HD float quad_inter(const QuadRow& a, const QuadCol& b) {
+  if (a.ux == a.ux && quad_col_is_para(b)) return para_inter(a, b);       // both parallelograms (a.ux is NaN otherwise)
   return quad_tri_inter(a, b.ox, b.oy, b.e1x, b.e1y, b.e2x, b.e2y, b.invD1, b.aD1)
        + quad_tri_inter(a, b.ox, b.oy, b.e2x, b.e2y, b.e3x, b.e3y, b.invD2, b.aD2);
 }
@@ -337,7 +404,12 @@ AIDET_HD void quad_prepare(const float* box8, QuadRow* row, QuadCol* col) {
   if (row) {
     for (int k = 0; k < 4; k++) { row->x[k] = x[k] - mx; row->y[k] = y[k] - my; }
     row->area = area; row->rad = rad; row->mx = mx; row->my = my;
-    row->pad[0] = row->pad[1] = row->pad[2] = row->pad[3] = 0.0f;
+    if (quad_is_para(row->x, row->y, mx, my, rad)) {               // least-squares half edges
+      row->ux = 0.25f * ((row->x[1] - row->x[0]) + (row->x[2] - row->x[3])); row->uy = 0.25f * ((row->y[1] - row->y[0]) + (row->y[2] - row->y[3]));
+      row->vx = 0.25f * ((row->x[3] - row->x[0]) + (row->x[2] - row->x[1])); row->vy = 0.25f * ((row->y[3] - row->y[0]) + (row->y[2] - row->y[1]));
+    } else {
+      row->ux = nanf(""); row->uy = row->vx = row->vy = 0.0f;
+    }
   }
   if (col) {
     col->ox = x[0]; col->oy = y[0];

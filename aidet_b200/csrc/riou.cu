@@ -19,6 +19,8 @@
 //               step as one straight-line block) or the per-lane early-out loop (sparse tiles).
 //   bound     : FP32 issue (157 instructions per pair, 85 % of the issue slots; no tensor-core
 //               shape); output traffic 4 B/pair is ~1/8 of HBM peak at the achieved rate.
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -59,8 +61,9 @@ enum { STORE_LOCAL = 0, STORE_PEERS = 1, STORE_MCAST = 2 };
 #endif
 constexpr int kRiouUnroll = AIDET_RIOU_UNROLL;
 
+// (the 8-point kind carries both the parallelogram and the general-quad arithmetic: 3 CTAs per SM, 80 registers)
 template <class K, int MODE, int STORE>
-__global__ void __launch_bounds__(kColsPerTile, AIDET_RIOU_MINB)
+__global__ void __launch_bounds__(kColsPerTile, K::FMT == 8 ? 3 : AIDET_RIOU_MINB)
 riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
                    const typename PairOp<K>::R* __restrict__ cols, int n,
                    OutSet outs, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
@@ -156,6 +159,142 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
   }
 }
 
+
+// ------------------------------------------------------------------ multi-GPU form with TMA tensor stores
+// The peer-store kernel above sends every value with its own 4-byte STG: 128 bytes per warp, row and peer -- small
+// NVLink packets, one store instruction per destination (r1: 594-678 GB/s of egress, the overlap lost 22 % at N = 2).
+// Here a CTA collects the (32 rows x 256 columns) tile in shared memory (conflict-free STS, one per pair as before) and ONE
+// thread hands it to the TMA unit: one cp.async.bulk.tensor.2d store per destination GPU (32 KB each, 1 KB rows, clipped
+// at the matrix edge by the tensor map), local copy included.  The LSU issues no global store at all, the copy engine
+// streams full-size NVLink packets, and the stores of tile t overlap the arithmetic of tile t+1 (two tile buffers,
+// bulk-group commit / wait_group.read before a buffer is rewritten).
+constexpr int kTmaTileRows = 32;
+
+struct TmaOuts { CUtensorMap map[kMaxPeers]; int n; };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int r0) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(r0),
+               "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class K, int MODE>
+__global__ void __launch_bounds__(kColsPerTile, 3)
+riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
+                       const typename PairOp<K>::R* __restrict__ cols, int n,
+                       const __grid_constant__ TmaOuts outs, int n_row_tiles, int n_tiles, int tiles_per_cta) {
+  using P = PairOp<K>;
+  using S = typename P::S; using R = typename P::R;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  float* otile = reinterpret_cast<float*>(dyn);                           // [2][kTmaTileRows][256]
+  S* stage = reinterpret_cast<S*>(dyn + 2 * kTmaTileRows * kColsPerTile * 4);   // [2][kTmaTileRows]
+  __shared__ __align__(8) uint64_t bar[2];
+
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(t_begin + tiles_per_cta, n_tiles);
+  if (t_begin >= t_end) return;
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_barrier_init(); }
+  __syncthreads();
+  auto issue = [&](int t, int buf) {      // thread 0 only
+    const int r0 = (t % n_row_tiles) * kTmaTileRows;
+    const uint32_t bytes = (uint32_t)(min(kTmaTileRows, m - r0) * (int)sizeof(S));
+    mbar_expect_tx(&bar[buf], bytes);
+    tma_load_1d(stage + buf * kTmaTileRows, rows + r0, bytes, &bar[buf]);
+  };
+  if (threadIdx.x == 0) issue(t_begin, 0);
+
+  int cur_ct = -1;
+  R me;
+  for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && t + 1 < t_end) issue(t + 1, buf ^ 1);
+    const int ct = t / n_row_tiles, rt = t % n_row_tiles;
+    if (ct != cur_ct) {
+      cur_ct = ct;
+      const int col = ct * kColsPerTile + threadIdx.x;
+      me = cols[col < n ? col : n - 1];                    // columns past n are computed and clipped by the tensor map
+    }
+    mbar_wait(&bar[buf], (it >> 1) & 1);
+    const int r0 = rt * kTmaTileRows;
+    const int nr = min(kTmaTileRows, m - r0);
+    const S* st = stage + buf * kTmaTileRows;
+    float* ot = otile + buf * (kTmaTileRows * kColsPerTile) + threadIdx.x;
+    int r = 0;
+    if constexpr (!std::is_same<K, HbbKind>::value) {
+      bool dual = false;
+      if (nr >= 2) dual = __any_sync(0xffffffffu, P::near(st[0], me)) && __any_sync(0xffffffffu, P::near(st[1], me));
+      if (dual) {
+#pragma unroll 1
+        for (; r + 2 <= nr; r += 2) {
+          const S sa = st[r], sb = st[r + 1];
+          const bool ha = P::near(sa, me), hb = P::near(sb, me);
+          const bool wa = __any_sync(0xffffffffu, ha), wb = __any_sync(0xffffffffu, hb);
+          float va = 0.0f, vb = 0.0f;
+          if (wa && wb) {
+            const float ia = K::inter(sa, me), ib = K::inter(sb, me);
+            va = ha ? finish_overlap(ia, sa.area, me.area, MODE) : 0.0f;
+            vb = hb ? finish_overlap(ib, sb.area, me.area, MODE) : 0.0f;
+          } else if (wa) {
+            va = ha ? finish_overlap(K::inter(sa, me), sa.area, me.area, MODE) : 0.0f;
+          } else if (wb) {
+            vb = hb ? finish_overlap(K::inter(sb, me), sb.area, me.area, MODE) : 0.0f;
+          }
+          ot[r * kColsPerTile] = va;
+          ot[(r + 1) * kColsPerTile] = vb;
+        }
+      }
+    }
+#pragma unroll kRiouUnroll
+    for (; r < nr; ++r) ot[r * kColsPerTile] = P::overlap(st[r], me, MODE);
+    // hand the tile to the copy engine: the writes above (generic proxy) become visible to the async proxy, then one
+    // thread issues a tensor store per destination; rows past m / columns past n are clipped by the tensor map
+    fence_proxy_async();
+    __syncthreads();                                        // tile complete; stage[buf] free for the load of tile t+2
+    if (threadIdx.x == 0) {
+      const float* src = otile + buf * (kTmaTileRows * kColsPerTile);
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q)
+        if (q < outs.n) tma_store_2d(&outs.map[q], src, ct * kColsPerTile, r0);
+      tma_commit();
+      tma_wait_read<1>();                                   // the stores of tile t-1 have read their buffer: it may be rewritten
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tma_wait_all<0>();                  // every store has completed before the CTA retires
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// (m, n) float32 row block at `base`, row stride ld elements -> tensor map with a (256 x 32) box.  false: not expressible.
+static bool make_out_map(CUtensorMap* map, float* base, int m, int n, long long ld) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  // strides and addresses in 16-byte units; the store clips at the tensor edge in 16-byte units as well (measured: with
+  // n % 4 == 2 the two floats after the row end were written), so rows must END on a 16-byte boundary too
+  if (!enc || (ld & 3) || (n & 3) || ((uintptr_t)base & 15)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)m};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kColsPerTile, (cuuint32_t)kTmaTileRows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class K>
 __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                            int n, int mode, float* __restrict__ out) {
@@ -204,6 +343,35 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   riou_prepare_both_kernel<K><<<ceil_div(m + n, 256), 256, 0, s>>>(a, m, b, n, rows, cols);
   const int sms = sm_count(device);
   const int n_col_tiles = ceil_div(n, kColsPerTile);
+  if (outs.n > 1 && !mcast) {
+    // several destinations (row-sharded multi-GPU form): tiles leave through TMA tensor stores when every destination
+    // is expressible as a tensor map (16-byte aligned base, row stride a multiple of 4 elements)
+    TmaOuts t{};
+    bool ok = true;
+    for (int q = 0; q < outs.n && ok; ++q) ok = make_out_map(&t.map[q], outs.p[q], m, n, ld);
+    if (ok) {
+      t.n = outs.n;
+      const int n_row_tiles = ceil_div(m, kTmaTileRows);
+      const long long n_tiles_ll = (long long)n_row_tiles * n_col_tiles;
+      if (n_tiles_ll > 0x7fffffffLL) { set_error("riou: problem too large (%lld tiles)", n_tiles_ll); return AIDET_EINVAL; }
+      const int n_tiles = (int)n_tiles_ll;
+      int grid = min(n_tiles, sms * 12);
+      const int tiles_per_cta = ceil_div(n_tiles, grid);
+      grid = ceil_div(n_tiles, tiles_per_cta);
+      const size_t smem = 2 * (size_t)kTmaTileRows * kColsPerTile * 4 + 2 * (size_t)kTmaTileRows * sizeof(S);
+      ProfScope prof(PROF_RIOU, s);
+      if (mode == MODE_IOF) {
+        AIDET_CUDA(cudaFuncSetAttribute(riou_matrix_tma_kernel<K, MODE_IOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        riou_matrix_tma_kernel<K, MODE_IOF><<<grid, kColsPerTile, smem, s>>>(rows, m, cols, n, t, n_row_tiles, n_tiles, tiles_per_cta);
+      } else {
+        AIDET_CUDA(cudaFuncSetAttribute(riou_matrix_tma_kernel<K, MODE_IOU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        riou_matrix_tma_kernel<K, MODE_IOU><<<grid, kColsPerTile, smem, s>>>(rows, m, cols, n, t, n_row_tiles, n_tiles, tiles_per_cta);
+      }
+      count_launch(2);
+      AIDET_CUDA(cudaGetLastError());
+      return AIDET_OK;
+    }
+  }
   int tile_rows = kMaxTileRows;
   while (tile_rows > 8 && (long long)ceil_div(m, tile_rows) * n_col_tiles < 8LL * sms) tile_rows >>= 1;
   const int n_row_tiles = ceil_div(m, tile_rows);

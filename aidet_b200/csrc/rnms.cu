@@ -265,7 +265,7 @@ struct NmsTile { int start, ng, r0, cq0, nr, g; };   // nr == 0: no tile left
 #define AIDET_NMS_MINB 4
 #endif
 template <class O, bool GE>
-__global__ void __launch_bounds__(kTileCols, AIDET_NMS_MINB)
+__global__ void __launch_bounds__(kTileCols, O::FMT == 8 ? 3 : AIDET_NMS_MINB)
 nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
                 const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
                 int n_groups, const float* __restrict__ thr, int n_thr, float one, int tile_rows,

@@ -156,3 +156,31 @@ def test_hbb_bbox_overlaps_reference_doctest_and_oracle(cuda):
         assert np.abs(got - ref).max() <= 1e-5
         al = bbox_overlaps(a[:533].to(cuda), b.to(cuda), mode=mode, is_aligned=True).cpu().numpy()
         assert np.abs(al - np.diag(O.hbb_overlaps(a[:533].numpy(), b.numpy(), mode=mode, plus_one=True))).max() <= 1e-5
+
+
+@pytest.mark.parametrize("m,n,fmt", [(300, 1028, 5), (33, 256, 5), (1, 4, 5), (700, 2000, 8), (257, 1030, 5), (64, 1023, 5)])
+def test_multi_destination_stores(cuda, m, n, fmt):
+    """aidet_riou_matrix_multi_f32 (the fused compute + all-gather kernel of the row-sharded form) with several LOCAL
+    destinations: every destination must hold exactly what the single-destination kernel writes.  n % 4 == 0 takes the
+    TMA tensor-store kernel (tiles clipped at the matrix edge by the tensor map -- in 16-byte units, hence the
+    condition), the other shapes the per-value peer-store kernel; rows past m and the padding columns of a wider
+    buffer must stay untouched either way."""
+    from aidet_b200.ops import functional as F
+    a, _ = synth.dota_boxes(m, side=400, seed=m)
+    b, _ = synth.dota_boxes(n, side=400, seed=n + 1)
+    if fmt == 8:
+        a, b = synth.thetaobb2pointobb(a).float(), synth.thetaobb2pointobb(b).float()
+    a, b = a.to(cuda), b.to(cuda)
+    want = F.riou_matrix(a, b)
+    ld = (n + 7) // 4 * 4 + 4                                        # a wider buffer: row stride > n, still 16-byte rows
+    bufs = [torch.full((m + 3, ld), -7.0, device=cuda) for _ in range(3)]
+    F.riou_matrix_multi(a, b, [t.data_ptr() for t in bufs], ld)
+    torch.cuda.synchronize()
+    for t in bufs:
+        assert torch.equal(t[:m, :n], want)
+        assert bool((t[m:] == -7.0).all()) and bool((t[:, n:] == -7.0).all())
+    if n % 4:                                                        # odd row stride: falls back to the per-value stores
+        bufs = [torch.full((m, n), -7.0, device=cuda) for _ in range(2)]
+        F.riou_matrix_multi(a, b, [t.data_ptr() for t in bufs], n)
+        for t in bufs:
+            assert torch.equal(t, want)
