@@ -27,9 +27,11 @@
 
 #if defined(__CUDACC__)
 #define AIDET_HD __host__ __device__ __forceinline__
+#define AIDET_HDM __host__ __device__ __forceinline__      // member functions
 #define AIDET_ALIGN16 __align__(16)
 #else
 #define AIDET_HD static inline
+#define AIDET_HDM inline
 #define AIDET_ALIGN16 alignas(16)
 #endif
 
@@ -339,22 +341,40 @@ AIDET_HD float para_edge(float px, float py, float dx, float rdx, float rdy, flo
   return rect_edge(px, -py * rdy, fabsf(rdy), 1.0f, -px * rdx, xo - ardx, xo + ardx, -xref - sx, -xref + sx, 0.5f * dx);
 }
 
-// a, b: both parallelograms (a.ux is not NaN; the caller checked b with quad_col_is_para).  Intersection area.
-AIDET_HD float para_inter(const QuadRow& a, const QuadCol& b) {
-  // B: centre (mx, my), half edges uB = (e1 + e2 - e3) / 4, vB = (e3 + e2 - e1) / 4 (least squares over the four corners)
-  const float ubx = 0.25f * (b.e1x + b.e2x - b.e3x), uby = 0.25f * (b.e1y + b.e2y - b.e3y);
-  const float vbx = 0.25f * (b.e3x + b.e2x - b.e1x), vby = 0.25f * (b.e3y + b.e2y - b.e1y);
-  const float det = ubx * vby - uby * vbx;                    // > 0 (CCW); 0 only for degenerate boxes (area 0 -> overlap 0)
-  const float rdet = frcp(det + 1e-30f);
-  // M^-1 = [vby -vbx; -uby ubx] / det: A's centre and half edges in B's frame (B = [-1,1]^2)
+AIDET_HD bool quad_col_is_para(const QuadCol& b) {
+  const float res = fabsf(b.e2x - b.e1x - b.e3x) + fabsf(b.e2y - b.e1y - b.e3y);
+  return res <= para_tolerance(b.mx, b.my, b.rad);
+}
+
+// Column box as the kernels keep it in REGISTERS for a whole column tile: the stored record plus what the parallelogram
+// path needs of it, derived once per tile instead of once per pair.
+//   centre = o + (cdx, cdy), half edges uB = (e1 + e2 - e3) / 4, vB = (e3 + e2 - e1) / 4 (least squares over the corners),
+//   M^-1 = [vBy -vBx; -uBy uBx] / det  (B = [-1,1]^2 in that frame); m00 is NaN when B is not a parallelogram.
+struct QuadReg : QuadCol {
+  float m00, m01, m10, m11, det, cdx, cdy;
+  AIDET_HDM QuadReg() {}
+  AIDET_HDM QuadReg(const QuadCol& b) : QuadCol(b) {
+    const float ubx = 0.25f * (b.e1x + b.e2x - b.e3x), uby = 0.25f * (b.e1y + b.e2y - b.e3y);
+    const float vbx = 0.25f * (b.e3x + b.e2x - b.e1x), vby = 0.25f * (b.e3y + b.e2y - b.e1y);
+    det = ubx * vby - uby * vbx;                              // > 0 (CCW); 0 only for degenerate boxes (area 0 -> overlap 0)
+    const float rdet = 1.0f / (det + 1e-30f);
+    m00 = quad_col_is_para(b) ? vby * rdet : nanf("");
+    m01 = -vbx * rdet; m10 = -uby * rdet; m11 = ubx * rdet;
+    cdx = 0.25f * (b.e1x + b.e2x + b.e3x); cdy = 0.25f * (b.e1y + b.e2y + b.e3y);
+  }
+};
+
+// a, b: both parallelograms (a.ux and b.m00 are not NaN).  Intersection area.
+AIDET_HD float para_inter(const QuadRow& a, const QuadReg& b) {
   // centres: the exact mean of the four corners on both sides -- (a.mx, a.my) is that mean ROUNDED (the corner offsets
   // carry the remainder), B's corners are o, o + e1, o + e2, o + e3
-  const float relx = (a.mx - b.ox) + (0.25f * ((a.x[0] + a.x[2]) + (a.x[1] + a.x[3])) - 0.25f * (b.e1x + b.e2x + b.e3x));
-  const float rely = (a.my - b.oy) + (0.25f * ((a.y[0] + a.y[2]) + (a.y[1] + a.y[3])) - 0.25f * (b.e1y + b.e2y + b.e3y));
-  float rx = (vby * relx - vbx * rely) * rdet;
-  const float ry = (ubx * rely - uby * relx) * rdet;
-  const float ux = (vby * a.ux - vbx * a.uy) * rdet + 1e-20f, uy = (ubx * a.uy - uby * a.ux) * rdet + 1e-20f;
-  const float vx = (vby * a.vx - vbx * a.vy) * rdet + 1e-20f, vy = (ubx * a.vy - uby * a.vx) * rdet + 1e-20f;
+  const float relx = (a.mx - b.ox) + (0.25f * ((a.x[0] + a.x[2]) + (a.x[1] + a.x[3])) - b.cdx);
+  const float rely = (a.my - b.oy) + (0.25f * ((a.y[0] + a.y[2]) + (a.y[1] + a.y[3])) - b.cdy);
+  // A's centre and half edges in B's frame
+  float rx = fmaf(b.m00, relx, b.m01 * rely);
+  const float ry = fmaf(b.m10, relx, b.m11 * rely);
+  const float ux = fmaf(b.m00, a.ux, b.m01 * a.uy) + 1e-20f, uy = fmaf(b.m10, a.ux, b.m11 * a.uy) + 1e-20f;
+  const float vx = fmaf(b.m00, a.vx, b.m01 * a.vy) + 1e-20f, vy = fmaf(b.m10, a.vx, b.m11 * a.vy) + 1e-20f;
   const float xref = fminf(fmaxf(rx, -1.0f), 1.0f);           // same shift as rect_inter: terms of the order of the smaller box
   rx -= xref;
   const float mx = rx - ux, my = ry - uy;
@@ -366,19 +386,21 @@ AIDET_HD float para_inter(const QuadRow& a, const QuadCol& b) {
   // edges p0->p1 (+du), p1->p2 (+dv), p2->p3 == -(p3->p2, +du), p3->p0 == -(p0->p3, +dv)
   const float iu = para_edge(p0x, p0y, dux, rux, ruy, xref) - para_edge(p3x, p3y, dux, rux, ruy, xref);
   const float iv = para_edge(p1x, p1y, dvx, rvx, rvy, xref) - para_edge(p0x, p0y, dvx, rvx, rvy, xref);
-  return det * fmaf(duy, iu, dvy * iv);
+  return b.det * fmaf(duy, iu, dvy * iv);
 }
 
-AIDET_HD bool quad_col_is_para(const QuadCol& b) {
-  const float res = fabsf(b.e2x - b.e1x - b.e3x) + fabsf(b.e2y - b.e1y - b.e3y);
-  return res <= para_tolerance(b.mx, b.my, b.rad);
-}
-
-AIDET_HD float quad_inter(const QuadRow& a, const QuadCol& b) {
-  if (a.ux == a.ux && quad_col_is_para(b)) return para_inter(a, b);       // both parallelograms (a.ux is NaN otherwise)
+AIDET_HD float quad_fan_inter(const QuadRow& a, const QuadCol& b) {
   return quad_tri_inter(a, b.ox, b.oy, b.e1x, b.e1y, b.e2x, b.e2y, b.invD1, b.aD1)
        + quad_tri_inter(a, b.ox, b.oy, b.e2x, b.e2y, b.e3x, b.e3y, b.invD2, b.aD2);
 }
+
+// register-resident column (kernels): the parallelogram test of the column was made when the record was loaded
+AIDET_HD float quad_inter(const QuadRow& a, const QuadReg& b) {
+  if (a.ux == a.ux && b.m00 == b.m00) return para_inter(a, b);            // both parallelograms (NaN otherwise)
+  return quad_fan_inter(a, b);
+}
+// stored column (aligned pairs, gradients, host simulation)
+AIDET_HD float quad_inter(const QuadRow& a, const QuadCol& b) { return quad_inter(a, QuadReg(b)); }
 
 AIDET_HD float quad_overlap(const QuadRow& a, const QuadCol& b, int mode) {
   float dx = a.mx - b.mx, dy = a.my - b.my, r = a.rad + b.rad;

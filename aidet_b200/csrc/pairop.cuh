@@ -6,8 +6,10 @@
 
 namespace aidet {
 
+// Row / Col: the prepared records as stored (staged in shared memory / read from global memory); Reg: the column record as
+// a kernel keeps it in registers for a whole column tile (constructible from Col; may carry derived values).
 struct RectKind {
-  using Row = RectRow; using Col = RectCol;
+  using Row = RectRow; using Col = RectCol; using Reg = RectCol;
   static constexpr int FMT = 5;
   __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return rect_inter(a, b); }
   __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { rect_prepare(p, r, c); }
@@ -15,9 +17,9 @@ struct RectKind {
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.cy; }
 };
 struct QuadKind {
-  using Row = QuadRow; using Col = QuadCol;
+  using Row = QuadRow; using Col = QuadCol; using Reg = QuadReg;
   static constexpr int FMT = 8;
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return quad_inter(a, b); }
+  __device__ static __forceinline__ float inter(const Row& a, const Reg& b) { return quad_inter(a, b); }
   __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { quad_prepare(p, r, c); }
   template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.mx; }
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.my; }
@@ -26,7 +28,7 @@ struct QuadKind {
 // fmt 4: axis-aligned (x1,y1,x2,y2) boxes with the legacy +1 pixel convention of mmdet/core/bbox/geometry.py:57-86
 // (bbox_overlaps) -- the same tiled kernel; this one is bound by the 4 B/pair result store, not by arithmetic.
 struct HbbKind {
-  using Row = HbbBox; using Col = HbbBox;
+  using Row = HbbBox; using Col = HbbBox; using Reg = HbbBox;
   static constexpr int FMT = 4;
   __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) {
     HbbBox b{p[0], p[1], p[2], p[3]};
@@ -40,13 +42,14 @@ struct HbbKind {
 template <class K>
 struct PairOp {
   using S = typename K::Row;   // staged (matrix row)
-  using R = typename K::Col;   // registers (matrix col)
+  using R = typename K::Col;   // matrix col as stored
+  using X = typename K::Reg;   // matrix col in registers
   // bounding circles meet (the early-out test of overlap())
-  __device__ static __forceinline__ bool near(const S& s, const R& r) {
+  __device__ static __forceinline__ bool near(const S& s, const X& r) {
     float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
     return !(fmaf(dx, dx, dy * dy) > rr * rr);
   }
-  __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) {
+  __device__ static __forceinline__ float overlap(const S& s, const X& r, int mode) {
     float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
     if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;
     return finish_overlap(K::inter(s, r), s.area, r.area, mode);
@@ -55,7 +58,7 @@ struct PairOp {
 
 template <>
 struct PairOp<HbbKind> {
-  using S = HbbBox; using R = HbbBox;
+  using S = HbbBox; using R = HbbBox; using X = HbbBox;
   __device__ static __forceinline__ float overlap(const S& s, const R& r, int mode) { return hbb_overlap(s, r, 1.0f, mode); }
 };
 

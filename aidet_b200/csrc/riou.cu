@@ -90,7 +90,7 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
   if (threadIdx.x == 0) issue(t_begin, 0);
 
   int cur_ct = -1;
-  R me;
+  typename P::X me;
   bool live = false;
   int col = 0;
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
@@ -163,12 +163,12 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
 // ------------------------------------------------------------------ multi-GPU form with TMA tensor stores
 // The peer-store kernel above sends every value with its own 4-byte STG: 128 bytes per warp, row and peer -- small
 // NVLink packets, one store instruction per destination (r1: 594-678 GB/s of egress, the overlap lost 22 % at N = 2).
-// Here a CTA collects the (32 rows x 256 columns) tile in shared memory (conflict-free STS, one per pair as before) and ONE
-// thread hands it to the TMA unit: one cp.async.bulk.tensor.2d store per destination GPU (32 KB each, 1 KB rows, clipped
+// Here a CTA collects the (16 rows x 256 columns) tile in shared memory (conflict-free STS, one per pair as before) and ONE
+// thread hands it to the TMA unit: one cp.async.bulk.tensor.2d store per destination GPU (16 KB each, 1 KB rows, clipped
 // at the matrix edge by the tensor map), local copy included.  The LSU issues no global store at all, the copy engine
 // streams full-size NVLink packets, and the stores of tile t overlap the arithmetic of tile t+1 (two tile buffers,
 // bulk-group commit / wait_group.read before a buffer is rewritten).
-constexpr int kTmaTileRows = 32;
+constexpr int kTmaTileRows = 16;      // 2 x 16 KB tile buffers: four CTAs per SM like the single-destination kernel
 
 struct TmaOuts { CUtensorMap map[kMaxPeers]; int n; };
 
@@ -182,7 +182,7 @@ template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile(
 template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <class K, int MODE>
-__global__ void __launch_bounds__(kColsPerTile, 3)
+__global__ void __launch_bounds__(kColsPerTile, K::FMT == 8 ? 3 : 4)
 riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
                        const typename PairOp<K>::R* __restrict__ cols, int n,
                        const __grid_constant__ TmaOuts outs, int n_row_tiles, int n_tiles, int tiles_per_cta) {
@@ -207,7 +207,7 @@ riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
   if (threadIdx.x == 0) issue(t_begin, 0);
 
   int cur_ct = -1;
-  R me;
+  typename P::X me;
   for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
     const int buf = it & 1;
     if (threadIdx.x == 0 && t + 1 < t_end) issue(t + 1, buf ^ 1);
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) riou_aligned_kernel(const float* __restri
   typename K::Row r; typename K::Col c;
   K::prepare(pa, &r, nullptr);
   K::prepare(pb, nullptr, &c);
-  out[i] = PairOp<K>::overlap(r, c, mode);
+  out[i] = PairOp<K>::overlap(r, typename K::Reg(c), mode);
 }
 
 // d overlap(a[i], b[i]) / d (box parameters) of both boxes, scaled by the upstream gradient: the backward of the aligned
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(256) riou_aligned_grad_kernel(const float* __r
 
 template <class K>
 static int launch_matrix(const float* a, int m, const float* b, int n, int mode, const OutSet& outs, long long ld,
-                         void* ws, int device, cudaStream_t s, bool mcast = false) {
+                         void* ws, int device, cudaStream_t s, bool mcast = false, bool force_tma = false) {
   using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
   S* rows = reinterpret_cast<S*>(ws);
@@ -343,7 +343,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   riou_prepare_both_kernel<K><<<ceil_div(m + n, 256), 256, 0, s>>>(a, m, b, n, rows, cols);
   const int sms = sm_count(device);
   const int n_col_tiles = ceil_div(n, kColsPerTile);
-  if (outs.n > 1 && !mcast) {
+  if ((outs.n > 1 || force_tma) && !mcast) {
     // several destinations (row-sharded multi-GPU form): tiles leave through TMA tensor stores when every destination
     // is expressible as a tensor map (16-byte aligned base, row stride a multiple of 4 elements)
     TmaOuts t{};
@@ -453,8 +453,8 @@ int aidet_riou_matrix_multi_f32(const float* a, int m, const float* b, int n, in
   outs.n = n_outs;
   if (int rc = set_device(device)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
-  return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s);
+  if (fmt == 5) return launch_matrix<RectKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s, false, true);
+  return launch_matrix<QuadKind>(a, m, b, n, mode, outs, ld_out, workspace, device, s, false, true);
 }
 
 int aidet_riou_matrix_mcast_f32(const float* a, int m, const float* b, int n, int fmt, int mode, float* out_mc,

@@ -80,7 +80,7 @@ assign_pass_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     mbar_expect_tx(&bar, bytes);
     tma_load_1d(&stage[0], rows + r0, bytes, &bar);
   }
-  R me;
+  typename P::X me;
   if (!FROM_MATRIX) me = cols[live ? col : n - 1];
   const bool ignored = live && ign_best && (unsigned)(ign_best[col] >> 32) > ign_thr_enc;
   const bool act = live && !ignored;

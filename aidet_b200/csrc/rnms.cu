@@ -31,7 +31,7 @@ namespace aidet {
 
 // ------------------------------------------------------------------ box kinds
 struct NmsRect {
-  using Row = RectRow; using Col = RectCol;
+  using Row = RectRow; using Col = RectCol; using Reg = RectCol;
   static constexpr int FMT = 5;
   __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { rect_prepare(p, r, c); }
   __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return rect_overlap(a, b, MODE_IOU); }
@@ -44,7 +44,7 @@ struct NmsRect {
   __device__ static __forceinline__ float area_c(const Col& b, float) { return b.area; }
 };
 struct NmsQuad {
-  using Row = QuadRow; using Col = QuadCol;
+  using Row = QuadRow; using Col = QuadCol; using Reg = QuadReg;
   static constexpr int FMT = 8;
   __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { quad_prepare(p, r, c); }
   __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return quad_overlap(a, b, MODE_IOU); }
@@ -52,12 +52,12 @@ struct NmsQuad {
     const float dx = a.mx - b.mx, dy = a.my - b.my, r = a.rad + b.rad;
     return fmaf(dx, dx, dy * dy) > r * r;
   }
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b, float) { return quad_inter(a, b); }
+  __device__ static __forceinline__ float inter(const Row& a, const Reg& b, float) { return quad_inter(a, b); }
   __device__ static __forceinline__ float area(const Row& a, float) { return a.area; }
   __device__ static __forceinline__ float area_c(const Col& b, float) { return b.area; }
 };
 struct NmsHbb {
-  using Row = HbbBox; using Col = HbbBox;
+  using Row = HbbBox; using Col = HbbBox; using Reg = HbbBox;
   static constexpr int FMT = 4;
   __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) {
     HbbBox b{p[0], p[1], p[2], p[3]};
@@ -80,7 +80,7 @@ struct NmsHbb {
 // (both boxes degenerate: IoU is defined 0 here, NaN > thr == false in the reference's HBB kernel) or far
 // above the denormal range.  `zero_hit` = what the comparison gives for IoU == 0.
 template <class O, bool GE>
-__device__ __forceinline__ bool nms_hit(const typename O::Row& a, const typename O::Col& b, float area_b, float one,
+__device__ __forceinline__ bool nms_hit(const typename O::Row& a, const typename O::Reg& b, float area_b, float one,
                                         float th, bool zero_hit) {
   if (O::disjoint(a, b)) return zero_hit;
   const float area_a = O::area(a, one);
@@ -325,7 +325,7 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
     const bool need = (c0 + 31 > d.r0) && (c0 < d.ng); // some column of the strip follows some row of the tile (warp-uniform)
     const int j = c0 + lane;
     const bool live = j < d.ng;
-    Col me;
+    typename O::Reg me;
     float area_me = 0.f;
     if (need) { me = cols[d.start + (live ? j : d.ng - 1)]; area_me = O::area_c(me, one); }
     mbar_wait(&bar[buf], (it >> 1) & 1);
@@ -787,7 +787,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     int u = blockIdx.x * kWarps + warp;
     const int u_hi = total, u_step = gridDim.x * kWarps;
     int cur_g = -1, cur_c = -1, start = 0, ng = 0;
-    Col me; float area_me = 0.f, th = 0.f; bool zero_hit = false;
+    typename O::Reg me; float area_me = 0.f, th = 0.f; bool zero_hit = false;
     while (u < u_hi) {
       int lo = 0, hi = n_groups;                                     // last g with sprefix[g] <= u
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sprefix[mid] <= u) lo = mid; else hi = mid; }
@@ -1078,8 +1078,9 @@ static bool coop_supported(int device) {
 // resident CTAs per SM of the fused kernel with `smem` bytes of dynamic shared memory (0: does not fit)
 static int fused_occupancy(void* fn, size_t smem) {
   if (smem > 200 * 1024) return 0;
-  if (smem > 48 * 1024 &&
-      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  // always opt in: the 48 KB default limit counts the kernel's static shared memory too (a 48 KB dynamic request
+  // alone is refused and the occupancy query then answers 0)
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max(smem, (size_t)48 * 1024)) != cudaSuccess) return 0;
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kFusedThreads, smem) != cudaSuccess) return 0;
   return occ;
