@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(256) nms_keys_kernel(const float* __restrict__
   if (i < 2 * n_groups) gbounds[i] = 0;          // [start | end) of every group, empty by default
   if (i >= n) return;
   uint32_t g = groups ? (uint32_t)groups[i] : 0u;
+  g = min(g, (uint32_t)n_groups);                // ids outside [0, n_groups): behind every group, never scanned
   keys[i] = ((uint64_t)g << 32) | (uint64_t)(~orderable(scores[i]));
   idx[i] = i;
   flags[i] = 0;
@@ -1147,7 +1148,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
     size_t cub_bytes = L.cub_bytes;
     AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
-                                               32 + group_bits(n_groups), s));
+                                               32 + group_bits(n_groups + 1), s));   // + 1: ids outside [0, n_groups) are clamped to n_groups and sort last
     nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
   }
   const int sms = sm_count(device);

@@ -161,22 +161,43 @@ def _nms_cuda(boxes, scores, groups, thr, n_groups):
     return F.nms_batched(boxes, scores, groups, thr, n_groups=n_groups, cmp_ge=False, plus_one=False)
 
 
+def _keep_mask(boxes, scores, groups, thr, n_groups, nms_fn):
+    """Batched NMS -> boolean keep mask over ALL boxes.  Boxes whose group id is `n_groups` (not this rank's share) are
+    never scanned and never kept.  With the CUDA library nothing touches the host: the kernel's (keep, n_keep) pair is
+    turned into a mask by an index_add on the device (entries past n_keep are garbage: they are clamped and add 0)."""
+    n = boxes.size(0)
+    if nms_fn is not None:                                   # tests: a host callable that returns keep indices
+        mask = torch.zeros(n, dtype=torch.bool, device=boxes.device)
+        ok = groups < n_groups
+        if bool(ok.any()):
+            idx = ok.nonzero().flatten()
+            mask[idx[nms_fn(boxes[idx].contiguous(), scores[idx].contiguous(), groups[idx].contiguous(), thr, n_groups)]] = True
+        return mask
+    from .ops import functional as F
+    keep, n_keep = F.nms_batched(boxes, scores, groups, thr, n_groups=n_groups, cmp_ge=False, plus_one=False, sync=False)
+    valid = (torch.arange(n, device=boxes.device) < n_keep).to(torch.int32)
+    hits = torch.zeros(n, dtype=torch.int32, device=boxes.device).index_add_(0, keep.clamp(0, n - 1), valid)
+    return hits > 0
+
+
 def scene_merge_nms(boxes, scores, labels, tile_ids, tile_origins, num_classes=15, tile_iou_thr=0.5, merge_thr=None,
                     group=None, nms_fn=None):
     """Per-tile NMS + cross-tile merge NMS of one scene, tiles sharded over the ranks.
 
     boxes (n, 5|8) in TILE coordinates, scores (n,), labels (n,) in [0, num_classes), tile_ids (n,) in
     [0, T); tile_origins (T, 2).  All inputs are replicated (every rank sees every detection -- they are
-    KBs); rank r runs the per-tile NMS of tiles t with t % G == r in one batched launch (groups =
-    tile x class), the survivors are translated to the scene frame and all-gathered, and the merge NMS
-    (groups = class, thresholds `merge_thr` (num_classes,), default dota.py:324) is sharded by class.
-    Suppression is `IoU > thr` in both stages (DOTA_devkit keeps `ovr <= thresh`).
+    KBs).  Stage 1: rank r runs the per-tile NMS of the tiles t with t % G == r in one batched launch (groups =
+    tile x class; the other ranks' detections carry an out-of-range group id, which the kernel sorts behind every
+    group and never scans).  Stage 2: the survivors are translated to the scene frame and the merge NMS (groups =
+    class, thresholds `merge_thr` (num_classes,), default dota.py:324) is sharded by class the same way.  Each stage
+    ends with ONE fixed-size all-reduce of the (n,) keep masks -- no ragged gathers, no size exchange, and no host
+    synchronisation before the final compaction.  Suppression is `IoU > thr` in both stages (DOTA_devkit keeps
+    `ovr <= thresh`).
 
     Returns (boxes (k, d) scene frame, scores (k,), labels (k,)) -- identical on every rank, ordered by
     (class, tile, original index) so the result does not depend on the world size.
     """
     world, rank = _world(group)
-    fn = nms_fn or _nms_cuda
     dev = boxes.device
     n_tiles = tile_origins.size(0)
     if merge_thr is None:
@@ -184,29 +205,26 @@ def scene_merge_nms(boxes, scores, labels, tile_ids, tile_origins, num_classes=1
     merge_thr = merge_thr.to(device=dev, dtype=torch.float32)
     labels = labels.long()
     tile_ids = tile_ids.long()
+
+    def exchange(mask):
+        if world == 1:
+            return mask
+        m = mask.to(torch.int32)
+        dist.all_reduce(m, group=group)                      # the ranks' masks are disjoint: the sum is their union
+        return m > 0
+
     # ---- stage 1: per-tile, per-class NMS on my tiles
-    mine = (tile_ids % world) == rank
-    idx = mine.nonzero().flatten()
-    if idx.numel():
-        g = (tile_ids[idx] * num_classes + labels[idx]).int()
-        keep = fn(boxes[idx].contiguous(), scores[idx].contiguous(), g, tile_iou_thr, n_tiles * num_classes)
-        surv = idx[keep]
-    else:
-        surv = idx
-    surv_all, _ = gather_ragged(surv, group)
-    surv_all, _ = torch.sort(surv_all)                      # original order: independent of the world size
-    sb = translate_to_scene(boxes[surv_all], tile_origins.to(dev)[tile_ids[surv_all]])
-    ss, sl = scores[surv_all], labels[surv_all]
-    # ---- stage 2: cross-tile merge, sharded by class
-    mine2 = ((sl % world) == rank).nonzero().flatten()
-    if mine2.numel():
-        keep2 = fn(sb[mine2].contiguous(), ss[mine2].contiguous(), sl[mine2].int(), merge_thr, num_classes)
-        kept = mine2[keep2]
-    else:
-        kept = mine2
-    kept_all, _ = gather_ragged(kept, group)
-    kept_all, _ = torch.sort(kept_all)
-    # class-major output (the reference writes one Task1_<class>.txt per class, dota.py:296-308)
-    order = torch.argsort(sl[kept_all], stable=True)
+    g1_all = n_tiles * num_classes
+    g1 = tile_ids * num_classes + labels
+    g1 = torch.where((tile_ids % world) == rank, g1, torch.full_like(g1, g1_all)).int()
+    surv = exchange(_keep_mask(boxes, scores, g1, tile_iou_thr, g1_all, nms_fn))
+    # ---- stage 2: cross-tile merge in the scene frame, sharded by class
+    sb = translate_to_scene(boxes, tile_origins.to(dev)[tile_ids])
+    g2 = torch.where(surv & ((labels % world) == rank), labels, torch.full_like(labels, num_classes)).int()
+    kept = exchange(_keep_mask(sb, scores, g2, merge_thr, num_classes, nms_fn))
+    # class-major output (the reference writes one Task1_<class>.txt per class, dota.py:296-308); the only host
+    # synchronisation of the call is this compaction
+    kept_all = kept.nonzero().flatten()
+    order = torch.argsort(labels[kept_all], stable=True)
     kept_all = kept_all[order]
-    return sb[kept_all], ss[kept_all], sl[kept_all]
+    return sb[kept_all], scores[kept_all], labels[kept_all]
