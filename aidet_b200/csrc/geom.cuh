@@ -80,73 +80,79 @@ struct AIDET_ALIGN16 HbbBox { float x1, y1, x2, y2; };
 
 // ------------------------------------------------- rect ^ rect (theta-OBB)
 
-// Edge integral described in the header comment for the edge p + tau * dir, tau in [0, L],
-// |dir| = 1 (tau is arc length, so no per-box reciprocal is needed: the crossing parameters
-// only use 1/cos and 1/sin of the RELATIVE angle, two MUFU.RCP per pair for all four edges).
-//   qy = -py / dir.y,  hr = H / |dir.y|        -> in-slab range  [qy - hr, qy + hr] ^ [0, L]
-//   qx = -px / dir.x,  a1 <= a2                -> x crossings    qx + a1, qx + a2
-//   x1st, x2nd : the box's x bounds in the order this direction meets them
-//   hdx = dir.x / 2
-// Inside [t0,t1] the clamp value is x1st before the first crossing, x2nd after the second and
-// x itself (taken at the middle of the piece) in between.  Every piece length is a difference
-// of clamped parameters, so an empty range contributes exactly 0 without a branch.
-AIDET_HD float rect_edge(float px, float qy, float hr, float L, float qx, float a1, float a2, float x1st,
+// clamp to [0, 1]: a modifier of the producing FADD / FMUL / FFMA on the device (.SAT) -- it costs no instruction, where
+// a clamp built from min / max costs two on the half-rate ALU pipe.  NaN -> 0 on both sides.
+#if defined(__CUDA_ARCH__)
+AIDET_HD float sat(float x) { return __saturatef(x); }
+#else
+AIDET_HD float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+#endif
+
+// Edge integral described in the header comment for the edge p + tau * D, tau in [0, 1] (D = the whole edge vector).
+// Parametrising by the edge fraction makes every clamp of a parameter to the edge a saturation:
+//   nrDy = -1 / D.y,  hr = H / |D.y|     -> in-slab range  [t0, t1] = sat(-py / D.y -+ hr)
+//   nrDx = -1 / D.x,  wr = W / |D.x|     -> x crossings    c1, c2 = -tpx / D.x -+ wr   (tpx: the start point's x about
+//                                           B's centre; px: the same point in the frame shifted by xref, see rect_inter)
+//   x1st, x2nd : the box's x bounds (shifted frame) in the order this direction meets them;  hdx = D.x / 2
+// Inside [t0, t1] the clamp value is x1st before the first crossing (length l_lo), x2nd after the second (l_hi) and x
+// itself (taken at the middle of the piece) in between.  Every piece length is a saturated difference of parameters in
+// [0, 1], so an empty range contributes exactly 0 without a branch: 2 min/max per edge (r1: 7).
+AIDET_HD float rect_edge(float px, float py, float tpx, float nrDy, float hr, float nrDx, float wr, float x1st,
                          float x2nd, float hdx) {
-  float t0 = fmaxf(qy - hr, 0.0f);
-  float t1 = fmaxf(fminf(qy + hr, L), t0);
-  float ta = fminf(fmaxf(qx + a1, t0), t1);
-  float tb = fminf(fmaxf(qx + a2, t0), t1);
-  float xmid = fmaf(hdx, ta + tb, px);
-  return fmaf(tb - ta, xmid, fmaf(t1 - tb, x2nd, (ta - t0) * x1st));
+  const float t0 = sat(fmaf(py, nrDy, -hr));
+  const float t1 = sat(fmaf(py, nrDy, hr));                      // >= t0: hr >= 0 and sat is monotonic
+  const float c1 = fmaf(tpx, nrDx, -wr), c2 = fmaf(tpx, nrDx, wr);
+  const float l_lo = sat(fminf(c1, t1) - t0);
+  const float l_hi = sat(t1 - fmaxf(c2, t0));
+  const float ta = t0 + l_lo, tb = t1 - l_hi;
+  const float xmid = fmaf(hdx, ta + tb, px);
+  return fmaf(tb - ta, xmid, fmaf(l_hi, x2nd, l_lo * x1st));
 }
 
 // Intersection area of A with B, in B's frame.
 AIDET_HD float rect_inter(const Rect& a, const Rect& b) {
   const float relx = a.cx - b.cx, rely = a.cy - b.cy;
-  // centre of A and its axis direction (cos, sin of the relative angle) in B's frame.  The tiny
-  // addend (applied last, so it cannot be absorbed) keeps both components non-zero -- parallel
-  // boxes would give 1/0 -- and is far below f32 resolution of any other value.
-  float rx = fmaf(b.c, relx, b.s * rely);
+  // centre of A and its axis direction (cos, sin of the relative angle) in B's frame
+  const float trx = fmaf(b.c, relx, b.s * rely);
   const float ry = fmaf(b.c, rely, -b.s * relx);
-  const float c = fmaf(a.c, b.c, a.s * b.s) + 1e-20f;
-  const float s = fmaf(a.s, b.c, -a.c * b.s) + 1e-20f;
+  const float c = fmaf(a.c, b.c, a.s * b.s);
+  const float s = fmaf(a.s, b.c, -a.c * b.s);
   // Shift x by xref = clamp(rx): the contour integral of a constant times 1[|y|<=H] dy over a
   // closed polygon is 0, so the result is unchanged, but every term is now of the order of the
   // SMALLER box, which keeps the rounding error relative to the intersection.
-  const float xref = fminf(fmaxf(rx, -b.W), b.W);
-  rx -= xref;                                     // B now spans [-xref - W, -xref + W] in x
-  const float ux = a.W * c, uy = a.W * s, vx = -a.H * s, vy = a.H * c;
-  // corners p0 = r-u-v, p1 = r+u-v, p3 = r-u+v  (CCW: p0,p1,p2,p3)
-  const float mx = rx - ux, my = ry - uy;
-  const float p0x = mx - vx, p0y = my - vy;
-  const float p3x = mx + vx, p3y = my + vy;
-  const float p1x = fmaf(2.0f, ux, p0x), p1y = fmaf(2.0f, uy, p0y);
-  const float rc = frcp(c), rs = frcp(s);
-  const float arc = fabsf(rc), ars = fabsf(rs);
-  // direction u = (c, s): y crossings use 1/s, x crossings 1/c
-  const float hr_u = b.H * ars, wr_u = b.W * arc, xo_u = -xref * rc;
-  const float ws_u = copysignf(b.W, c);
-  // direction v = (-s, c): y crossings use 1/c, x crossings -1/s
-  const float hr_v = b.H * arc, wr_v = b.W * ars, xo_v = xref * rs;
-  const float ws_v = copysignf(b.W, -s);
+  const float xref = fminf(fmaxf(trx, -b.W), b.W);
+  const float rx = trx - xref;                    // B now spans [-xref - W, -xref + W] in x
+  // edge vectors Du = 2 W (c, s), Dv = 2 H (-s, c).  The tiny addend keeps every component non-zero (parallel boxes
+  // would give 1/0; rect_prepare keeps W, H >= 1e-9) and is far below f32 resolution of any component it does not replace.
   const float Lu = a.W + a.W, Lv = a.H + a.H;
-  const float hc = 0.5f * c, hs = -0.5f * s;
-  const float a1u = xo_u - wr_u, a2u = xo_u + wr_u, x1u = -xref - ws_u, x2u = -xref + ws_u;
-  const float a1v = xo_v - wr_v, a2v = xo_v + wr_v, x1v = -xref - ws_v, x2v = -xref + ws_v;
-  // edges p0->p1 (+u), p1->p2 (+v), p2->p3 == -(p3->p2, +u), p3->p0 == -(p0->p3, +v)
-  const float iu = rect_edge(p0x, -p0y * rs, hr_u, Lu, -p0x * rc, a1u, a2u, x1u, x2u, hc)
-                 - rect_edge(p3x, -p3y * rs, hr_u, Lu, -p3x * rc, a1u, a2u, x1u, x2u, hc);
-  const float iv = rect_edge(p1x, -p1y * rc, hr_v, Lv, p1x * rs, a1v, a2v, x1v, x2v, hs)
-                 - rect_edge(p0x, -p0y * rc, hr_v, Lv, p0x * rs, a1v, a2v, x1v, x2v, hs);
-  return fmaf(s, iu, c * iv);                     // dy/dtau = s along u, c along v
+  const float dux = fmaf(Lu, c, 1e-28f), duy = fmaf(Lu, s, 1e-28f);
+  const float dvx = fmaf(-Lv, s, 1e-28f), dvy = fmaf(Lv, c, 1e-28f);
+  // corners p0 = r - Du/2 - Dv/2, p1 = p0 + Du, p3 = p0 + Dv  (CCW: p0,p1,p2,p3); t*: x about B's centre
+  const float p0x = fmaf(-0.5f, dux, fmaf(-0.5f, dvx, rx)), p0y = fmaf(-0.5f, duy, fmaf(-0.5f, dvy, ry));
+  const float p3x = p0x + dvx, p3y = p0y + dvy;
+  const float p1x = p0x + dux, p1y = p0y + duy;
+  const float t0x = p0x + xref, t3x = p3x + xref, t1x = p1x + xref;
+  const float rux = frcp(dux), ruy = frcp(duy), rvx = frcp(dvx), rvy = frcp(dvy);
+  const float hr_u = b.H * fabsf(ruy), wr_u = b.W * fabsf(rux), ws_u = copysignf(b.W, dux);
+  const float hr_v = b.H * fabsf(rvy), wr_v = b.W * fabsf(rvx), ws_v = copysignf(b.W, dvx);
+  const float x1u = -xref - ws_u, x2u = ws_u - xref, x1v = -xref - ws_v, x2v = ws_v - xref;
+  const float hu = 0.5f * dux, hv = 0.5f * dvx;
+  // edges p0->p1 (+Du), p1->p2 (+Dv), p2->p3 == -(p3->p2, +Du), p3->p0 == -(p0->p3, +Dv)
+  const float iu = rect_edge(p0x, p0y, t0x, -ruy, hr_u, -rux, wr_u, x1u, x2u, hu)
+                 - rect_edge(p3x, p3y, t3x, -ruy, hr_u, -rux, wr_u, x1u, x2u, hu);
+  const float iv = rect_edge(p1x, p1y, t1x, -rvy, hr_v, -rvx, wr_v, x1v, x2v, hv)
+                 - rect_edge(p0x, p0y, t0x, -rvy, hr_v, -rvx, wr_v, x1v, x2v, hv);
+  return fmaf(duy, iu, dvy * iv);                 // dy over the whole edge
 }
 
 // den is a box area or a union of two: either 0 (degenerate boxes -> overlap 0) or far above
 // the denormal range, so the plain MUFU.RCP (<= 1 ulp) replaces a guarded division.
 AIDET_HD float finish_overlap(float inter, float area_a, float area_b, int mode) {
-  inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_b));
-  float den = (mode == MODE_IOF) ? area_a : (mode == MODE_IOF_B) ? area_b : (area_a + area_b - inter);
-  return den > 0.0f ? inter * frcp(den) : 0.0f;
+  inter = fminf(inter, fminf(area_a, area_b));
+  const float den = (mode == MODE_IOF) ? area_a : (mode == MODE_IOF_B) ? area_b : (area_a + area_b - inter);
+  // the final saturation is the lower clamp of `inter` (rounding can leave it a hair below 0) and the guard of
+  // den == 0 (then inter <= 0: 0 * inf = NaN -> 0, negative * inf = -inf -> 0)
+  return sat(inter * frcp(den));
 }
 
 AIDET_HD float rect_overlap(const Rect& a, const Rect& b, int mode) {
@@ -162,7 +168,8 @@ AIDET_HD void rect_prepare(const float* box5, Rect* out) {
   float W = 0.5f * w, H = 0.5f * h;
   out->cx = box5[0]; out->cy = box5[1];
   out->c = (float)cos(th); out->s = (float)sin(th);
-  out->W = W; out->H = H; out->area = w * h;
+  out->W = fmaxf(W, 1e-9f); out->H = fmaxf(H, 1e-9f);     // the edge vectors stay invertible (rect_inter); the area does not move
+  out->area = w * h;
   out->rad = sqrtf(W * W + H * H) * 1.000001f + 1e-6f;
 }
 AIDET_HD void rect_prepare(const float* box5, Rect* row, Rect* col) {
@@ -336,9 +343,8 @@ AIDET_HD bool quad_is_para(const float* x, const float* y, float mx, float my, f
 // Edge integral of rect_edge for the edge p + t d, t in [0, 1], against the square |x|,|y| <= 1 shifted by xref in x;
 // rdx, rdy = 1/d.x, 1/d.y (never 0 / inf: the caller adds 1e-20 to the components).
 AIDET_HD float para_edge(float px, float py, float dx, float rdx, float rdy, float xref) {
-  const float ardx = fabsf(rdx), sx = copysignf(1.0f, dx);
-  const float xo = -xref * rdx;
-  return rect_edge(px, -py * rdy, fabsf(rdy), 1.0f, -px * rdx, xo - ardx, xo + ardx, -xref - sx, -xref + sx, 0.5f * dx);
+  const float sx = copysignf(1.0f, dx);
+  return rect_edge(px, py, px + xref, -rdy, fabsf(rdy), -rdx, fabsf(rdx), -xref - sx, sx - xref, 0.5f * dx);
 }
 
 AIDET_HD bool quad_col_is_para(const QuadCol& b) {
