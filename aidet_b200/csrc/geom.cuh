@@ -88,20 +88,20 @@ AIDET_HD float sat(float x) { return __saturatef(x); }
 AIDET_HD float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 #endif
 
-// Edge integral described in the header comment for the edge p + tau * D, tau in [0, 1] (D = the whole edge vector).
-// Parametrising by the edge fraction makes every clamp of a parameter to the edge a saturation:
-//   nrDy = -1 / D.y,  hr = H / |D.y|     -> in-slab range  [t0, t1] = sat(-py / D.y -+ hr)
-//   nrDx = -1 / D.x,  wr = W / |D.x|     -> x crossings    c1, c2 = -tpx / D.x -+ wr   (tpx: the start point's x about
-//                                           B's centre; px: the same point in the frame shifted by xref, see rect_inter)
-//   x1st, x2nd : the box's x bounds (shifted frame) in the order this direction meets them;  hdx = D.x / 2
+// Edge integral described in the header comment for the edge p + tau * D, tau in [0, 1] (D = the whole edge vector,
+// p in the frame shifted by xref, see rect_inter).  Parametrising by the edge fraction makes every clamp of a parameter
+// to the edge a saturation:
+//   nrDy = -1 / D.y,  hr = H / |D.y|          -> in-slab range  [t0, t1] = sat(-py / D.y -+ hr)
+//   nrDx = -1 / D.x,  k1 = x1st / D.x, k2 ..  -> x crossings    c1, c2 = (x1st - px) / D.x, (x2nd - px) / D.x
+//   x1st, x2nd : the box's x bounds in the order this direction meets them;  hdx = D.x / 2
 // Inside [t0, t1] the clamp value is x1st before the first crossing (length l_lo), x2nd after the second (l_hi) and x
 // itself (taken at the middle of the piece) in between.  Every piece length is a saturated difference of parameters in
 // [0, 1], so an empty range contributes exactly 0 without a branch: 2 min/max per edge (r1: 7).
-AIDET_HD float rect_edge(float px, float py, float tpx, float nrDy, float hr, float nrDx, float wr, float x1st,
+AIDET_HD float rect_edge(float px, float py, float nrDy, float hr, float nrDx, float k1, float k2, float x1st,
                          float x2nd, float hdx) {
   const float t0 = sat(fmaf(py, nrDy, -hr));
   const float t1 = sat(fmaf(py, nrDy, hr));                      // >= t0: hr >= 0 and sat is monotonic
-  const float c1 = fmaf(tpx, nrDx, -wr), c2 = fmaf(tpx, nrDx, wr);
+  const float c1 = fmaf(px, nrDx, k1), c2 = fmaf(px, nrDx, k2);
   const float l_lo = sat(fminf(c1, t1) - t0);
   const float l_hi = sat(t1 - fmaxf(c2, t0));
   const float ta = t0 + l_lo, tb = t1 - l_hi;
@@ -109,41 +109,66 @@ AIDET_HD float rect_edge(float px, float py, float tpx, float nrDy, float hr, fl
   return fmaf(tb - ta, xmid, fmaf(l_hi, x2nd, l_lo * x1st));
 }
 
-// Intersection area of A with B, in B's frame.
-AIDET_HD float rect_inter(const Rect& a, const Rect& b) {
+// The box that is transformed ("A", a matrix row), as the overlap-matrix kernels stage it (48 B): full edge lengths and
+// their reciprocals are per-box constants, so a pair needs only the two reciprocals of the RELATIVE angle's cos / sin
+// (MUFU.RCP occupies its issue port far longer than an FMUL: four per pair cost 6 % of the kernel).
+struct AIDET_ALIGN16 RectA {
+  float cx, cy, rad, harea;      // centre, circumradius (as Rect), HALF the area: the overlap is a ratio, and the edge
+                                 // integrals below come out as half the intersection (half edge vectors)
+  float c, s;                    // cos, sin of theta
+  float W, H;                    // half extents (>= 1e-9)
+  float iLu, iLv;                // 1 / 2W, 1 / 2H
+  float pad0, pad1;
+};
+
+// HALF the intersection area of A with B, in B's frame.
+AIDET_HD float rect_inter_half(const RectA& a, const Rect& b) {
   const float relx = a.cx - b.cx, rely = a.cy - b.cy;
-  // centre of A and its axis direction (cos, sin of the relative angle) in B's frame
+  // centre of A and its axis direction (cos, sin of the relative angle) in B's frame.  The tiny addend (applied last, so
+  // it cannot be absorbed) keeps both components non-zero -- parallel boxes would give 1/0 -- and is far below f32
+  // resolution of any other value.
   const float trx = fmaf(b.c, relx, b.s * rely);
   const float ry = fmaf(b.c, rely, -b.s * relx);
-  const float c = fmaf(a.c, b.c, a.s * b.s);
-  const float s = fmaf(a.s, b.c, -a.c * b.s);
-  // Shift x by xref = clamp(rx): the contour integral of a constant times 1[|y|<=H] dy over a
-  // closed polygon is 0, so the result is unchanged, but every term is now of the order of the
-  // SMALLER box, which keeps the rounding error relative to the intersection.
-  const float xref = fminf(fmaxf(trx, -b.W), b.W);
+  const float c = fmaf(a.c, b.c, a.s * b.s) + 1e-20f;
+  const float s = fmaf(a.s, b.c, -a.c * b.s) + 1e-20f;
+  // Shift x by xref ~ clamp(rx, -W, W): the contour integral of a constant times 1[|y|<=H] dy over a closed polygon is
+  // 0, so the result does not depend on xref, but every term is now of the order of the SMALLER box, which keeps the
+  // rounding error relative to the intersection.  (b.W * (2 sat(rx / 2W + 1/2) - 1): the clamp as a saturation;
+  // 1 / 2W depends on the column box only and is hoisted out of the row loop.)
+  const float i2W = 0.5f * frcp(b.W);
+  const float xref = fmaf(b.W + b.W, sat(fmaf(trx, i2W, 0.5f)), -b.W);
   const float rx = trx - xref;                    // B now spans [-xref - W, -xref + W] in x
-  // edge vectors Du = 2 W (c, s), Dv = 2 H (-s, c).  The tiny addend keeps every component non-zero (parallel boxes
-  // would give 1/0; rect_prepare keeps W, H >= 1e-9) and is far below f32 resolution of any component it does not replace.
-  const float Lu = a.W + a.W, Lv = a.H + a.H;
-  const float dux = fmaf(Lu, c, 1e-28f), duy = fmaf(Lu, s, 1e-28f);
-  const float dvx = fmaf(-Lv, s, 1e-28f), dvy = fmaf(Lv, c, 1e-28f);
-  // corners p0 = r - Du/2 - Dv/2, p1 = p0 + Du, p3 = p0 + Dv  (CCW: p0,p1,p2,p3); t*: x about B's centre
-  const float p0x = fmaf(-0.5f, dux, fmaf(-0.5f, dvx, rx)), p0y = fmaf(-0.5f, duy, fmaf(-0.5f, dvy, ry));
-  const float p3x = p0x + dvx, p3y = p0y + dvy;
-  const float p1x = p0x + dux, p1y = p0y + duy;
-  const float t0x = p0x + xref, t3x = p3x + xref, t1x = p1x + xref;
-  const float rux = frcp(dux), ruy = frcp(duy), rvx = frcp(dvx), rvy = frcp(dvy);
-  const float hr_u = b.H * fabsf(ruy), wr_u = b.W * fabsf(rux), ws_u = copysignf(b.W, dux);
-  const float hr_v = b.H * fabsf(rvy), wr_v = b.W * fabsf(rvx), ws_v = copysignf(b.W, dvx);
+  // half edge vectors hu = W (c, s), hv = H (-s, c); reciprocals of the components of the WHOLE edge vectors 2 hu, 2 hv
+  const float rc = frcp(c), rs = frcp(s);
+  const float hux = a.W * c, huy = a.W * s, hvx = -a.H * s, hvy = a.H * c;
+  const float rux = a.iLu * rc, ruy = a.iLu * rs, rvx = -a.iLv * rs, rvy = a.iLv * rc;
+  // corners p0 = r - hu - hv, p1 = p0 + 2 hu, p3 = p0 + 2 hv  (CCW: p0,p1,p2,p3)
+  const float mx = rx - hux, my = ry - huy;
+  const float p0x = mx - hvx, p0y = my - hvy;
+  const float p3x = mx + hvx, p3y = my + hvy;
+  const float p1x = fmaf(2.0f, hux, p0x), p1y = fmaf(2.0f, huy, p0y);
+  // B's x bounds in the order each direction meets them, and their crossing parameters relative to -px / D.x
+  const float ws_u = copysignf(b.W, hux), ws_v = copysignf(b.W, hvx);
   const float x1u = -xref - ws_u, x2u = ws_u - xref, x1v = -xref - ws_v, x2v = ws_v - xref;
-  const float hu = 0.5f * dux, hv = 0.5f * dvx;
-  // edges p0->p1 (+Du), p1->p2 (+Dv), p2->p3 == -(p3->p2, +Du), p3->p0 == -(p0->p3, +Dv)
-  const float iu = rect_edge(p0x, p0y, t0x, -ruy, hr_u, -rux, wr_u, x1u, x2u, hu)
-                 - rect_edge(p3x, p3y, t3x, -ruy, hr_u, -rux, wr_u, x1u, x2u, hu);
-  const float iv = rect_edge(p1x, p1y, t1x, -rvy, hr_v, -rvx, wr_v, x1v, x2v, hv)
-                 - rect_edge(p0x, p0y, t0x, -rvy, hr_v, -rvx, wr_v, x1v, x2v, hv);
-  return fmaf(duy, iu, dvy * iv);                 // dy over the whole edge
+  const float hr_u = b.H * fabsf(ruy), k1u = x1u * rux, k2u = x2u * rux;
+  const float hr_v = b.H * fabsf(rvy), k1v = x1v * rvx, k2v = x2v * rvx;
+  // edges p0->p1 (+2hu), p1->p2 (+2hv), p2->p3 == -(p3->p2, +2hu), p3->p0 == -(p0->p3, +2hv)
+  const float iu = rect_edge(p0x, p0y, -ruy, hr_u, -rux, k1u, k2u, x1u, x2u, hux)
+                 - rect_edge(p3x, p3y, -ruy, hr_u, -rux, k1u, k2u, x1u, x2u, hux);
+  const float iv = rect_edge(p1x, p1y, -rvy, hr_v, -rvx, k1v, k2v, x1v, x2v, hvx)
+                 - rect_edge(p0x, p0y, -rvy, hr_v, -rvx, k1v, k2v, x1v, x2v, hvx);
+  return fmaf(huy, iu, hvy * iv);                 // half of dy over the whole edge
 }
+
+// A given as a stored Rect (NMS, aligned pairs, gradients): the row constants are derived per pair
+AIDET_HD RectA rect_as_row(const Rect& r) {
+  RectA a;
+  a.cx = r.cx; a.cy = r.cy; a.rad = r.rad; a.harea = 0.5f * r.area; a.c = r.c; a.s = r.s;
+  a.W = r.W; a.H = r.H; a.iLu = 0.5f * frcp(r.W); a.iLv = 0.5f * frcp(r.H);
+  a.pad0 = a.pad1 = 0.0f;
+  return a;
+}
+AIDET_HD float rect_inter(const Rect& a, const Rect& b) { const float h = rect_inter_half(rect_as_row(a), b); return h + h; }
 
 // den is a box area or a union of two: either 0 (degenerate boxes -> overlap 0) or far above
 // the denormal range, so the plain MUFU.RCP (<= 1 ulp) replaces a guarded division.
@@ -171,6 +196,11 @@ AIDET_HD void rect_prepare(const float* box5, Rect* out) {
   out->W = fmaxf(W, 1e-9f); out->H = fmaxf(H, 1e-9f);     // the edge vectors stay invertible (rect_inter); the area does not move
   out->area = w * h;
   out->rad = sqrtf(W * W + H * H) * 1.000001f + 1e-6f;
+}
+AIDET_HD void rect_prepare(const float* box5, RectA* row, Rect* col) {
+  Rect r; rect_prepare(box5, &r);
+  if (row) { *row = rect_as_row(r); row->iLu = 0.5f / r.W; row->iLv = 0.5f / r.H; }
+  if (col) *col = r;
 }
 AIDET_HD void rect_prepare(const float* box5, Rect* row, Rect* col) {
   Rect r; rect_prepare(box5, &r);
@@ -344,7 +374,8 @@ AIDET_HD bool quad_is_para(const float* x, const float* y, float mx, float my, f
 // rdx, rdy = 1/d.x, 1/d.y (never 0 / inf: the caller adds 1e-20 to the components).
 AIDET_HD float para_edge(float px, float py, float dx, float rdx, float rdy, float xref) {
   const float sx = copysignf(1.0f, dx);
-  return rect_edge(px, py, px + xref, -rdy, fabsf(rdy), -rdx, fabsf(rdx), -xref - sx, sx - xref, 0.5f * dx);
+  const float x1 = -xref - sx, x2 = sx - xref;
+  return rect_edge(px, py, -rdy, fabsf(rdy), -rdx, x1 * rdx, x2 * rdx, x1, x2, 0.5f * dx);
 }
 
 AIDET_HD bool quad_col_is_para(const QuadCol& b) {

@@ -9,9 +9,12 @@ namespace aidet {
 // Row / Col: the prepared records as stored (staged in shared memory / read from global memory); Reg: the column record as
 // a kernel keeps it in registers for a whole column tile (constructible from Col; may carry derived values).
 struct RectKind {
-  using Row = RectRow; using Col = RectCol; using Reg = RectCol;
+  using Row = RectA; using Col = RectCol; using Reg = RectCol;   // rows carry their per-box constants (48 B)
   static constexpr int FMT = 5;
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return rect_inter(a, b); }
+  // inter / area_row / area_col: on a common scale (here: halves -- the edge integrals of geom.cuh come out halved)
+  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return rect_inter_half(a, b); }
+  __device__ static __forceinline__ float area_row(const Row& a) { return a.harea; }
+  __device__ static __forceinline__ float area_col(const Col& b) { return 0.5f * b.area; }
   __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { rect_prepare(p, r, c); }
   template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.cx; }
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.cy; }
@@ -20,6 +23,8 @@ struct QuadKind {
   using Row = QuadRow; using Col = QuadCol; using Reg = QuadReg;
   static constexpr int FMT = 8;
   __device__ static __forceinline__ float inter(const Row& a, const Reg& b) { return quad_inter(a, b); }
+  __device__ static __forceinline__ float area_row(const Row& a) { return a.area; }
+  __device__ static __forceinline__ float area_col(const Reg& b) { return b.area; }
   __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { quad_prepare(p, r, c); }
   template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.mx; }
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.my; }
@@ -52,7 +57,7 @@ struct PairOp {
   __device__ static __forceinline__ float overlap(const S& s, const X& r, int mode) {
     float dx = K::cx(s) - K::cx(r), dy = K::cy(s) - K::cy(r), rr = s.rad + r.rad;
     if (fmaf(dx, dx, dy * dy) > rr * rr) return 0.0f;
-    return finish_overlap(K::inter(s, r), s.area, r.area, mode);
+    return finish_overlap(K::inter(s, r), K::area_row(s), K::area_col(r), mode);
   }
 };
 
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(256) riou_prepare_both_kernel(const float* __r
   if (is_row) rows[i] = r; else cols[i - m] = c;
 }
 
-static inline size_t record_bytes(int fmt) { return (fmt == 8) ? 64 : (fmt == 4 ? 16 : 32); }
+// upper bound of a prepared record (row records of theta-OBBs are 48 B, column records 32 B)
+static inline size_t record_bytes(int fmt) { return (fmt == 8) ? 64 : (fmt == 4 ? 16 : 48); }
 
 }  // namespace aidet

@@ -140,12 +140,12 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
           float va = 0.0f, vb = 0.0f;
           if (wa && wb) {
             const float ia = K::inter(sa, me), ib = K::inter(sb, me);
-            va = ha ? finish_overlap(ia, sa.area, me.area, MODE) : 0.0f;
-            vb = hb ? finish_overlap(ib, sb.area, me.area, MODE) : 0.0f;
+            va = ha ? finish_overlap(ia, K::area_row(sa), K::area_col(me), MODE) : 0.0f;
+            vb = hb ? finish_overlap(ib, K::area_row(sb), K::area_col(me), MODE) : 0.0f;
           } else if (wa) {
-            va = ha ? finish_overlap(K::inter(sa, me), sa.area, me.area, MODE) : 0.0f;
+            va = ha ? finish_overlap(K::inter(sa, me), K::area_row(sa), K::area_col(me), MODE) : 0.0f;
           } else if (wb) {
-            vb = hb ? finish_overlap(K::inter(sb, me), sb.area, me.area, MODE) : 0.0f;
+            vb = hb ? finish_overlap(K::inter(sb, me), K::area_row(sb), K::area_col(me), MODE) : 0.0f;
           }
           put(va);
           put(vb);
@@ -235,12 +235,12 @@ riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
           float va = 0.0f, vb = 0.0f;
           if (wa && wb) {
             const float ia = K::inter(sa, me), ib = K::inter(sb, me);
-            va = ha ? finish_overlap(ia, sa.area, me.area, MODE) : 0.0f;
-            vb = hb ? finish_overlap(ib, sb.area, me.area, MODE) : 0.0f;
+            va = ha ? finish_overlap(ia, K::area_row(sa), K::area_col(me), MODE) : 0.0f;
+            vb = hb ? finish_overlap(ib, K::area_row(sb), K::area_col(me), MODE) : 0.0f;
           } else if (wa) {
-            va = ha ? finish_overlap(K::inter(sa, me), sa.area, me.area, MODE) : 0.0f;
+            va = ha ? finish_overlap(K::inter(sa, me), K::area_row(sa), K::area_col(me), MODE) : 0.0f;
           } else if (wb) {
-            vb = hb ? finish_overlap(K::inter(sb, me), sb.area, me.area, MODE) : 0.0f;
+            vb = hb ? finish_overlap(K::inter(sb, me), K::area_row(sb), K::area_col(me), MODE) : 0.0f;
           }
           ot[r * kColsPerTile] = va;
           ot[(r + 1) * kColsPerTile] = vb;
@@ -405,7 +405,7 @@ using namespace aidet;
 extern "C" {
 
 size_t aidet_riou_workspace_bytes(int m, int n, int fmt) {
-  size_t rec = (fmt == 8) ? 64 : (fmt == 4 ? 16 : 32);
+  size_t rec = record_bytes(fmt);
   return align_up((size_t)(m > 0 ? m : 0) * rec, 128) + align_up((size_t)(n > 0 ? n : 0) * rec, 128) + 128;
 }
 
