@@ -121,8 +121,16 @@ struct AIDET_ALIGN16 RectA {
   float pad0, pad1;
 };
 
+// The box whose frame is used ("B", a matrix column) as the kernels keep it in REGISTERS for a whole column tile: the
+// stored record plus what depends on it alone, derived once per tile instead of once per pair.
+struct RectB : Rect {
+  float W2, i2W, harea;          // 2W, 1 / 2W, area / 2
+  AIDET_HDM RectB() {}
+  AIDET_HDM RectB(const Rect& b) : Rect(b) { W2 = b.W + b.W; i2W = 0.5f * frcp(b.W); harea = 0.5f * b.area; }
+};
+
 // HALF the intersection area of A with B, in B's frame.
-AIDET_HD float rect_inter_half(const RectA& a, const Rect& b) {
+AIDET_HD float rect_inter_half(const RectA& a, const RectB& b) {
   const float relx = a.cx - b.cx, rely = a.cy - b.cy;
   // centre of A and its axis direction (cos, sin of the relative angle) in B's frame.  The tiny addend (applied last, so
   // it cannot be absorbed) keeps both components non-zero -- parallel boxes would give 1/0 -- and is far below f32
@@ -133,10 +141,8 @@ AIDET_HD float rect_inter_half(const RectA& a, const Rect& b) {
   const float s = fmaf(a.s, b.c, -a.c * b.s) + 1e-20f;
   // Shift x by xref ~ clamp(rx, -W, W): the contour integral of a constant times 1[|y|<=H] dy over a closed polygon is
   // 0, so the result does not depend on xref, but every term is now of the order of the SMALLER box, which keeps the
-  // rounding error relative to the intersection.  (b.W * (2 sat(rx / 2W + 1/2) - 1): the clamp as a saturation;
-  // 1 / 2W depends on the column box only and is hoisted out of the row loop.)
-  const float i2W = 0.5f * frcp(b.W);
-  const float xref = fmaf(b.W + b.W, sat(fmaf(trx, i2W, 0.5f)), -b.W);
+  // rounding error relative to the intersection.  (b.W * (2 sat(rx / 2W + 1/2) - 1): the clamp as a saturation.)
+  const float xref = fmaf(b.W2, sat(fmaf(trx, b.i2W, 0.5f)), -b.W);
   const float rx = trx - xref;                    // B now spans [-xref - W, -xref + W] in x
   // half edge vectors hu = W (c, s), hv = H (-s, c); reciprocals of the components of the WHOLE edge vectors 2 hu, 2 hv
   const float rc = frcp(c), rs = frcp(s);
@@ -168,7 +174,7 @@ AIDET_HD RectA rect_as_row(const Rect& r) {
   a.pad0 = a.pad1 = 0.0f;
   return a;
 }
-AIDET_HD float rect_inter(const Rect& a, const Rect& b) { const float h = rect_inter_half(rect_as_row(a), b); return h + h; }
+AIDET_HD float rect_inter(const Rect& a, const Rect& b) { const float h = rect_inter_half(rect_as_row(a), RectB(b)); return h + h; }
 
 // den is a box area or a union of two: either 0 (degenerate boxes -> overlap 0) or far above
 // the denormal range, so the plain MUFU.RCP (<= 1 ulp) replaces a guarded division.

@@ -9,12 +9,12 @@ namespace aidet {
 // Row / Col: the prepared records as stored (staged in shared memory / read from global memory); Reg: the column record as
 // a kernel keeps it in registers for a whole column tile (constructible from Col; may carry derived values).
 struct RectKind {
-  using Row = RectA; using Col = RectCol; using Reg = RectCol;   // rows carry their per-box constants (48 B)
+  using Row = RectA; using Col = RectCol; using Reg = RectB;     // rows carry their per-box constants (48 B)
   static constexpr int FMT = 5;
   // inter / area_row / area_col: on a common scale (here: halves -- the edge integrals of geom.cuh come out halved)
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b) { return rect_inter_half(a, b); }
+  __device__ static __forceinline__ float inter(const Row& a, const Reg& b) { return rect_inter_half(a, b); }
   __device__ static __forceinline__ float area_row(const Row& a) { return a.harea; }
-  __device__ static __forceinline__ float area_col(const Col& b) { return 0.5f * b.area; }
+  __device__ static __forceinline__ float area_col(const Reg& b) { return b.harea; }
   __device__ static __forceinline__ void prepare(const float* p, Row* r, Col* c) { rect_prepare(p, r, c); }
   template <class T> __device__ static __forceinline__ float cx(const T& t) { return t.cx; }
   template <class T> __device__ static __forceinline__ float cy(const T& t) { return t.cy; }

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kColsPerTile, K::FMT == 8 ? 3 : AIDET_RIOU_MIN
 riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
                    const typename PairOp<K>::R* __restrict__ cols, int n,
                    OutSet outs, long long ld, int tile_rows, int n_row_tiles, int n_tiles,
-                   int tiles_per_cta) {
+                   int tiles_per_cta, float* __restrict__ scratch) {
   using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
   __shared__ __align__(128) S stage[2][kMaxTileRows];
@@ -108,8 +108,15 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     const int nr = min(tile_rows, m - r0);
     long long off = (long long)r0 * ld + col;        // advanced by one row per iteration
     const S* st = &stage[buf][0];
+    // single destination: a running pointer; lanes of columns past n write a scratch line (step 0) instead of
+    // branching around every store
+    float* pa = live ? outs.p[0] + off : scratch + threadIdx.x;
+    const long long step = live ? ld : 0;
     auto put = [&](float v) {
-      if (live) {
+      if (STORE == STORE_LOCAL) {
+        __stcs(pa, v);
+        pa += step;
+      } else if (live) {
         if (STORE == STORE_PEERS) {
 #pragma unroll
           for (int q = 0; q < kMaxPeers; ++q) if (q < outs.n) __stcs(outs.p[q] + off, v);
@@ -340,6 +347,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
   using S = typename P::S; using R = typename P::R;
   S* rows = reinterpret_cast<S*>(ws);
   R* cols = reinterpret_cast<R*>(reinterpret_cast<char*>(ws) + align_up((size_t)m * sizeof(S), 128));
+  float* scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(cols) + align_up((size_t)n * sizeof(R), 128));   // 1 KB
   riou_prepare_both_kernel<K><<<ceil_div(m + n, 256), 256, 0, s>>>(a, m, b, n, rows, cols);
   const int sms = sm_count(device);
   const int n_col_tiles = ceil_div(n, kColsPerTile);
@@ -387,7 +395,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
     ProfScope prof(PROF_RIOU, s);
 #define AIDET_LAUNCH_RIOU(MODE_, STORE_)                                                                        \
   riou_matrix_kernel<K, MODE_, STORE_><<<grid, kColsPerTile, 0, s>>>(rows, m, cols, n, outs, ld, tile_rows,     \
-                                                                      n_row_tiles, n_tiles, tiles_per_cta)
+                                                                      n_row_tiles, n_tiles, tiles_per_cta, scratch)
     if (mcast)           { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_MCAST); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_MCAST); }
     else if (outs.n > 1) { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_PEERS); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_PEERS); }
     else                 { if (mode == MODE_IOF) AIDET_LAUNCH_RIOU(MODE_IOF, STORE_LOCAL); else AIDET_LAUNCH_RIOU(MODE_IOU, STORE_LOCAL); }
@@ -406,7 +414,7 @@ extern "C" {
 
 size_t aidet_riou_workspace_bytes(int m, int n, int fmt) {
   size_t rec = record_bytes(fmt);
-  return align_up((size_t)(m > 0 ? m : 0) * rec, 128) + align_up((size_t)(n > 0 ? n : 0) * rec, 128) + 128;
+  return align_up((size_t)(m > 0 ? m : 0) * rec, 128) + align_up((size_t)(n > 0 ? n : 0) * rec, 128) + 1024 + 128;   // + scratch line
 }
 
 int aidet_riou_matrix_f32(const float* a, int m, const float* b, int n, int fmt, int mode, float* out,
