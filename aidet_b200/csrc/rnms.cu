@@ -31,17 +31,18 @@ namespace aidet {
 
 // ------------------------------------------------------------------ box kinds
 struct NmsRect {
-  using Row = RectRow; using Col = RectCol; using Reg = RectCol;
+  // rows (the box that is transformed) carry their per-box constants (48 B RectA), columns are Rect records that a lane
+  // keeps in registers as RectB; intersection and areas are on the common HALF scale of geom.cuh: rect_inter_half
+  using Row = RectA; using Col = Rect; using Reg = RectB;
   static constexpr int FMT = 5;
   __device__ static __forceinline__ void prepare(const float* p, float, Row* r, Col* c) { rect_prepare(p, r, c); }
-  __device__ static __forceinline__ float overlap(const Row& a, const Col& b, float) { return rect_overlap(a, b, MODE_IOU); }
   __device__ static __forceinline__ bool disjoint(const Row& a, const Col& b) {
     const float dx = a.cx - b.cx, dy = a.cy - b.cy, r = a.rad + b.rad;
     return fmaf(dx, dx, dy * dy) > r * r;
   }
-  __device__ static __forceinline__ float inter(const Row& a, const Col& b, float) { return rect_inter(a, b); }
-  __device__ static __forceinline__ float area(const Row& a, float) { return a.area; }
-  __device__ static __forceinline__ float area_c(const Col& b, float) { return b.area; }
+  __device__ static __forceinline__ float inter(const Row& a, const Reg& b, float) { return rect_inter_half(a, b); }
+  __device__ static __forceinline__ float area(const Row& a, float) { return a.harea; }
+  __device__ static __forceinline__ float area_c(const Reg& b, float) { return b.harea; }
 };
 struct NmsQuad {
   using Row = QuadRow; using Col = QuadCol; using Reg = QuadReg;
@@ -1042,12 +1043,13 @@ static int group_bits(int n_groups) { int b = 0; while ((1LL << b) < (long long)
 
 static NmsLayout nms_layout(int n, int n_groups, int fmt, size_t cub_bytes) {
   NmsLayout L;
-  size_t rec = (fmt == 8) ? 64 : (fmt == 5 ? 32 : 16);
+  const size_t rec = (fmt == 8) ? 64 : (fmt == 5 ? 48 : 16);            // row records
+  const size_t rec_c = (fmt == 8) ? 64 : (fmt == 5 ? 32 : 0);           // column records (fmt 4: the row records serve)
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 128); return o; };
   L.keys_in = take((size_t)n * 8); L.keys_out = take((size_t)n * 8);
   L.idx_in = take((size_t)n * 4); L.order = take((size_t)n * 4);
-  L.rows = take((size_t)n * rec); L.cols = take(fmt == 8 ? (size_t)n * rec : 0);
+  L.rows = take((size_t)n * rec); L.cols = take((size_t)n * rec_c);
   L.gbounds = take((size_t)n_groups * 8); L.prefix = take((size_t)(n_groups + 3) * 4);
   L.flags = take((size_t)n + 16);
   L.pitch32 = 4LL * ((n + 127) / 128);                       // multiple of 4 words: rows are 16 B aligned (TMA bulk copies of the fused scan)
