@@ -36,7 +36,12 @@ def merge_thresholds(task='obb', classwise=True):
     return torch.tensor([table[c] if classwise else 0.3 for c in DOTA_CLASSES], dtype=torch.float32)
 
 
+SOLO = "solo"        # group argument: treat this rank as a world of one (every rank works on its own data, no collective)
+
+
 def _world(group):
+    if isinstance(group, str) and group == SOLO:
+        return 1, 0
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
     return 1, 0
