@@ -262,7 +262,8 @@ struct NmsTile { int start, ng, r0, cq0, nr, g; };   // nr == 0: no tile left
 // size).  Thread 0 is the scheduler: while the CTA works on tile k it draws the ticket of tile k+1, skips tiles
 // left of the diagonal, and starts the TMA copy of its row records into the other staging buffer.
 // 4 resident CTAs per SM (<= 64 registers).  A dual-row step like the overlap-matrix kernel's was measured here and
-// is slower (one dense 16384-box group: mask 0.780 vs 0.763 ms): the ballot per row already breaks the chains.
+// is no faster (one dense 16384-box group: r1 0.780 vs 0.763 ms, r2 with the saturation arithmetic 0.897 vs 0.893 ms
+// per call): the ballot per row already breaks the chains.
 #ifndef AIDET_NMS_MINB
 #define AIDET_NMS_MINB 4
 #endif
@@ -1150,7 +1151,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
     size_t cub_bytes = L.cub_bytes;
     AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
-                                               32 + group_bits(n_groups + 1), s));   // + 1: ids outside [0, n_groups) are clamped to n_groups and sort last
+                                               32 + (groups ? group_bits(n_groups + 1) : 0), s));   // + 1: ids outside [0, n_groups) are clamped to n_groups and sort last
     nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
   }
   const int sms = sm_count(device);
