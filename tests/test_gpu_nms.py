@@ -50,6 +50,17 @@ def test_thresholds(cuda, thr):
     _compare(boxes, scores, thr, inds)
 
 
+@pytest.mark.parametrize("n,side,thr", [(20000, 300, 0.1), (20000, 500, 0.3), (20000, 16384, 0.5), (9000, 500, 0.1)])
+def test_large_single_group(cuda, n, side, thr):
+    """One group beyond the fused kernel's 8192 boxes: radix sort + ticketed mask + the scan kernel that jumps over runs of
+    dead 32-row blocks (crowded set: most blocks die early), walks live blocks with the prefetch (sparse set: every block
+    lives) and reads columns beyond its 16384-column panel (n = 20000)."""
+    boxes, scores = synth.dota_boxes(n, side=side, seed=27)
+    inds = thetaobb_nms(torch.cat([boxes, scores[:, None]], 1).to(cuda), thr)[1]
+    kept, _ = _compare(boxes, scores, thr, inds)
+    print("n=%d side=%d: %d kept" % (n, side, kept))
+
+
 def test_pointobb_nms(cuda):
     boxes, scores = synth.dota_boxes(1200, side=512, seed=22)
     p8 = synth.thetaobb2pointobb(boxes)
