@@ -93,6 +93,20 @@ __device__ __forceinline__ bool nms_hit(const typename O::Row& a, const typename
   return den > 0.0f ? h : zero_hit;
 }
 
+// nms_hit for "IoU > thr" inside a DENSE block (the caller's probe found every lane's bounding circle meeting the block's
+// first and last row): no per-pair circle test and no early-out branch, and the comparison as
+//     inter (1 + thr) > thr area_a + thr area_b          (k1 = 1 + thr, thb = thr area_b: per column)
+// -- 3 instructions after the clamp of `inter` to the smaller area (which keeps zero-area boxes from suppressing anything:
+// inter <= 0 there).  A pair whose circles are disjoint after all yields inter = 0 or rounding noise ~1e-7 of the areas,
+// far below thr (area_a + area_b) for the thresholds the caller admits (thr >= 1e-4).
+template <class O>
+__device__ __forceinline__ bool nms_hit_dense(const typename O::Row& a, const typename O::Reg& b, float area_b, float one,
+                                              float th, float k1, float thb) {
+  const float area_a = O::area(a, one);
+  const float inter = fminf(O::inter(a, b, one), fminf(area_a, area_b));
+  return inter * k1 > fmaf(th, area_a, thb);
+}
+
 // ------------------------------------------------------------------ 1. keys
 __device__ __forceinline__ uint32_t orderable(float f) {      // ascending uint <=> ascending float
   uint32_t u = __float_as_uint(f);
@@ -339,11 +353,25 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
         const int lim = min(32, d.nr - rb);
         uint32_t word = 0;
         if (above) {                                   // the common case: no per-row diagonal tests
+          bool dense = false;
+          if constexpr (!GE && O::FMT != 4)
+            dense = th >= 1e-4f && __all_sync(0xffffffffu, live && !O::disjoint(st[rb], me) && !O::disjoint(st[rb + lim - 1], me));
+          if (dense) {
+            if constexpr (!GE && O::FMT != 4) {
+              const float k1 = 1.0f + th, thb = th * area_me;
 #pragma unroll 2
-          for (int k = 0; k < lim; ++k) {
-            const bool hit = nms_hit<O, GE>(st[rb + k], me, area_me, one, th, zero_hit);
-            const uint32_t b = __ballot_sync(0xffffffffu, hit && live);
-            if (lane == k) word = b;
+              for (int k = 0; k < lim; ++k) {
+                const uint32_t b = __ballot_sync(0xffffffffu, nms_hit_dense<O>(st[rb + k], me, area_me, one, th, k1, thb));
+                if (lane == k) word = b;
+              }
+            }
+          } else {
+#pragma unroll 2
+            for (int k = 0; k < lim; ++k) {
+              const bool hit = nms_hit<O, GE>(st[rb + k], me, area_me, one, th, zero_hit);
+              const uint32_t b = __ballot_sync(0xffffffffu, hit && live);
+              if (lane == k) word = b;
+            }
           }
         } else {
           for (int k = 0; k < lim; ++k) {
