@@ -136,9 +136,25 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
       // Probe: do the first two rows of the tile both have a lane whose bounding circles meet this warp's columns?
       // Dense tiles then take the dual-row loop, sparse tiles the plain per-lane early-out loop below (both give
       // identical values; the probe only picks the faster schedule).
-      bool dual = false;
-      if (nr >= 2) dual = __any_sync(0xffffffffu, P::near(st[0], me)) && __any_sync(0xffffffffu, P::near(st[1], me));
-      if (dual) {
+      bool dual = false, solid = false;
+      if (nr >= 2) {
+        const bool n0 = P::near(st[0], me), n1 = P::near(st[1], me);
+        dual = __any_sync(0xffffffffu, n0) && __any_sync(0xffffffffu, n1);
+        // solid: every lane's bounding circle meets the tile's first two and last rows -- the dense set.  Those tiles run
+        // without the per-pair circle test, its votes and the final select (7 % of the instructions): a pair whose circles
+        // are disjoint after all still gets its edge integrals, which give 0 or rounding noise ~1e-7 of the smaller area
+        // (the same as a pair whose circles meet and whose boxes do not).
+        solid = __all_sync(0xffffffffu, n0 && n1 && P::near(st[nr - 1], me));
+      }
+      if (solid) {
+#pragma unroll 1
+        for (; r + 2 <= nr; r += 2) {
+          const S sa = st[r], sb = st[r + 1];
+          const float ia = K::inter(sa, me), ib = K::inter(sb, me);
+          put(finish_overlap(ia, K::area_row(sa), K::area_col(me), MODE));
+          put(finish_overlap(ib, K::area_row(sb), K::area_col(me), MODE));
+        }
+      } else if (dual) {
 #pragma unroll 1
         for (; r + 2 <= nr; r += 2) {
           const S sa = st[r], sb = st[r + 1];
@@ -231,9 +247,21 @@ riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     float* ot = otile + buf * (kTmaTileRows * kColsPerTile) + threadIdx.x;
     int r = 0;
     if constexpr (!std::is_same<K, HbbKind>::value) {
-      bool dual = false;
-      if (nr >= 2) dual = __any_sync(0xffffffffu, P::near(st[0], me)) && __any_sync(0xffffffffu, P::near(st[1], me));
-      if (dual) {
+      bool dual = false, solid = false;
+      if (nr >= 2) {
+        const bool n0 = P::near(st[0], me), n1 = P::near(st[1], me);
+        dual = __any_sync(0xffffffffu, n0) && __any_sync(0xffffffffu, n1);
+        solid = __all_sync(0xffffffffu, n0 && n1 && P::near(st[nr - 1], me));       // see riou_matrix_kernel
+      }
+      if (solid) {
+#pragma unroll 1
+        for (; r + 2 <= nr; r += 2) {
+          const S sa = st[r], sb = st[r + 1];
+          const float ia = K::inter(sa, me), ib = K::inter(sb, me);
+          ot[r * kColsPerTile] = finish_overlap(ia, K::area_row(sa), K::area_col(me), MODE);
+          ot[(r + 1) * kColsPerTile] = finish_overlap(ib, K::area_row(sb), K::area_col(me), MODE);
+        }
+      } else if (dual) {
 #pragma unroll 1
         for (; r + 2 <= nr; r += 2) {
           const S sa = st[r], sb = st[r + 1];
