@@ -191,7 +191,11 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
 // at the matrix edge by the tensor map), local copy included.  The LSU issues no global store at all, the copy engine
 // streams full-size NVLink packets, and the stores of tile t overlap the arithmetic of tile t+1 (two tile buffers,
 // bulk-group commit / wait_group.read before a buffer is rewritten).
-constexpr int kTmaTileRows = 16;      // 2 x 16 KB tile buffers: four CTAs per SM like the single-destination kernel
+constexpr int kTmaTileRows = 16;      // 16 KB tile buffers: four CTAs per SM like the single-destination kernel
+#ifndef AIDET_TMA_OBUFS
+#define AIDET_TMA_OBUFS 4             // tile buffers per CTA (stores in flight + 1); N = 2 on one box: 309 / 310 / 329 Gpairs/s with 2 / 3 / 4
+#endif
+constexpr int kTmaOutBufs = AIDET_TMA_OBUFS;
 
 struct TmaOuts { CUtensorMap map[kMaxPeers]; int n; };
 
@@ -212,8 +216,8 @@ riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
   using P = PairOp<K>;
   using S = typename P::S; using R = typename P::R;
   extern __shared__ __align__(128) unsigned char dyn[];
-  float* otile = reinterpret_cast<float*>(dyn);                           // [2][kTmaTileRows][256]
-  S* stage = reinterpret_cast<S*>(dyn + 2 * kTmaTileRows * kColsPerTile * 4);   // [2][kTmaTileRows]
+  float* otile = reinterpret_cast<float*>(dyn);                           // [kTmaOutBufs][kTmaTileRows][256]
+  S* stage = reinterpret_cast<S*>(dyn + kTmaOutBufs * kTmaTileRows * kColsPerTile * 4);   // [2][kTmaTileRows]
   __shared__ __align__(8) uint64_t bar[2];
 
   const int t_begin = blockIdx.x * tiles_per_cta;
@@ -244,7 +248,8 @@ riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     const int r0 = rt * kTmaTileRows;
     const int nr = min(kTmaTileRows, m - r0);
     const S* st = stage + buf * kTmaTileRows;
-    float* ot = otile + buf * (kTmaTileRows * kColsPerTile) + threadIdx.x;
+    const int ob = it % kTmaOutBufs;
+    float* ot = otile + ob * (kTmaTileRows * kColsPerTile) + threadIdx.x;
     int r = 0;
     if constexpr (!std::is_same<K, HbbKind>::value) {
       bool dual = false, solid = false;
@@ -289,12 +294,12 @@ riou_matrix_tma_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
     fence_proxy_async();
     __syncthreads();                                        // tile complete; stage[buf] free for the load of tile t+2
     if (threadIdx.x == 0) {
-      const float* src = otile + buf * (kTmaTileRows * kColsPerTile);
+      const float* src = otile + ob * (kTmaTileRows * kColsPerTile);
 #pragma unroll
       for (int q = 0; q < kMaxPeers; ++q)
         if (q < outs.n) tma_store_2d(&outs.map[q], src, ct * kColsPerTile, r0);
       tma_commit();
-      tma_wait_read<1>();                                   // the stores of tile t-1 have read their buffer: it may be rewritten
+      tma_wait_read<kTmaOutBufs - 1>();                     // the stores of the tile that used the next buffer have read it: it may be rewritten
     }
     __syncthreads();
   }
@@ -394,7 +399,7 @@ static int launch_matrix(const float* a, int m, const float* b, int n, int mode,
       int grid = min(n_tiles, sms * 12);
       const int tiles_per_cta = ceil_div(n_tiles, grid);
       grid = ceil_div(n_tiles, tiles_per_cta);
-      const size_t smem = 2 * (size_t)kTmaTileRows * kColsPerTile * 4 + 2 * (size_t)kTmaTileRows * sizeof(S);
+      const size_t smem = (size_t)kTmaOutBufs * kTmaTileRows * kColsPerTile * 4 + 2 * (size_t)kTmaTileRows * sizeof(S);
       ProfScope prof(PROF_RIOU, s);
       if (mode == MODE_IOF) {
         AIDET_CUDA(cudaFuncSetAttribute(riou_matrix_tma_kernel<K, MODE_IOF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
