@@ -107,6 +107,25 @@ __device__ __forceinline__ bool nms_hit_dense(const typename O::Row& a, const ty
   return inter * k1 > fmaf(th, area_a, thb);
 }
 
+// The 32 greedy decisions of one diagonal block: keep_k = !init_k && no kept row j < k has bit k set in its diagonal word
+// D_j (upper triangular: D_j only holds bits > j).  The sequential form costs ~40 cycles per decision in dependent ALU /
+// predicate latency (measured: 0.7 us per block whether the words come from shuffles or from shared memory).  Here the
+// triangular system is solved by fixed-point iteration over all 32 rows at once: K <- ~(init | OR_{j in K} D_j), one
+// redux.or per round, starting from "every undecided row is kept".  After t rounds the decisions of rows < t are final
+// (row k depends on rows < k only), so it terminates within 33 rounds with the unique solution -- the greedy result --
+// and in practice within a few: one round when nothing overlaps, two when the first row suppresses the rest.
+// init: warp-uniform; dmine: the diagonal word of row `lane` (anything for rows that init marks).
+__device__ __forceinline__ uint32_t greedy_block(uint32_t init, uint32_t dmine, int lane) {
+  uint32_t K = ~init;
+  for (;;) {
+    const uint32_t R = init | __reduce_or_sync(0xffffffffu, ((K >> lane) & 1u) ? dmine : 0u);
+    const uint32_t Kn = ~R;
+    if (Kn == K) break;
+    K = Kn;
+  }
+  return K;
+}
+
 // ------------------------------------------------------------------ 1. keys
 __device__ __forceinline__ uint32_t orderable(float f) {      // ascending uint <=> ascending float
   uint32_t u = __float_as_uint(f);
@@ -462,12 +481,7 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
       const uint32_t d = pan[lane * kScanPW];               // diagonal half-word of row 32b + lane (0 past the end)
       uint32_t cur = removed[b];
       if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);   // positions past the group end
-      uint32_t keep = 0;
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const uint32_t dk = __shfl_sync(0xffffffffu, d, k);
-        if (!(cur & (1u << k))) { keep |= 1u << k; cur |= dk; }
-      }
+      const uint32_t keep = greedy_block(cur, d, lane);
       if (lane == 0) { keep_word = keep; s_next = nhw; }
     }
     __syncthreads();
@@ -610,6 +624,7 @@ constexpr int kFusedThreads = 256;
 constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp unit
 constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
 constexpr int kScanHelpers = kFusedThreads / 32 - 2;
+constexpr int kSoloBlocks = 16;           // groups of <= 16 blocks (512 boxes): scanned by one warp from shared memory
 constexpr int kPanelBlocks = 64;           // groups of <= 64 blocks (2048 boxes): the chain's words live in a 32 KB panel
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -897,6 +912,48 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     const int D = min(kScanSlotsMax, (use_panel ? ring_words - nhw * 128 : ring_words) / slot_words);   // >= 2 (host)
     const uint32_t* mgrp = mask32 + (long long)(start + 32 * g) * pitch32;
     __syncthreads();                                                   // previous group done with the barriers / s_keep
+    if (nhw <= kSoloBlocks) {
+      // ---- small group (<= 512 boxes: a class of a per-image problem): its whole upper triangle (<= 17 KB) is copied into
+      //      shared memory by all warps, then ONE warp scans it with no cross-warp hand-off at all -- per block the 32
+      //      greedy decisions plus one redux.or per later word; lane w keeps the removed bits of block w in a register.
+      //      (The warp-specialised form below pays ~0.9 us per block in flag round trips on such groups: C2 11.6 us.)
+      uint32_t* tri = ring;                                            // block b at tri + 32 (b nhw - b (b - 1) / 2)
+      for (int b = warp; b < nhw; b += kWarps) {
+        const uint4* src = reinterpret_cast<const uint4*>(mgrp + ((long long)b * pitch32 + b) * 32);
+        uint4* dst = reinterpret_cast<uint4*>(tri + 32 * (b * nhw - b * (b - 1) / 2));
+        for (int i = lane; i < (nhw - b) * 8; i += 32) dst[i] = __ldcg(src + i);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t rem = 0;                                              // lane w: rows of block w suppressed so far
+        for (int b = 0; b < nhw; ++b) {
+          const int rows_b = min(32, ng - 32 * b);
+          const uint32_t* blk = tri + 32 * (b * nhw - b * (b - 1) / 2);
+          uint32_t cur = __shfl_sync(0xffffffffu, rem, b);
+          if (rows_b < 32) cur |= ~0u << rows_b;
+          uint32_t keep = 0;
+          if (cur != ~0u) {
+            keep = greedy_block(cur, blk[lane], lane);                 // diagonal word of row 32 b + lane
+            const bool kept = (keep >> lane) & 1u;
+            for (int w = b + 1; w < nhw; w += 4) {                     // kept rows' words w .. w+3 -> four independent redux.or
+              uint32_t v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = (kept && w + q < nhw) ? blk[(w + q - b) * 32 + lane] : 0u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t r = __reduce_or_sync(0xffffffffu, v[q]);
+                if (lane == w + q) rem |= r;
+              }
+            }
+          }
+          if (lane == 0) s_keep[b] = keep;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < ng; i += kFusedThreads)
+        if ((s_keep[i >> 5] >> (i & 31)) & 1u) flags[order[start + i]] = 1;
+      continue;
+    }
     if (tid < kScanSlotsMax) { mbar_init(&bar_full[tid], 1); mbar_init(&bar_k[tid], 1); fence_barrier_init(); }
     for (int h = tid; h < nhw; h += kFusedThreads) { s_removed[h] = 0u; s_keep[h] = 0u; }
     if (tid < 8) s_hprog[tid] = 0u;
@@ -935,6 +992,8 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       //      from the panel that was loaded once (no barrier probe per block: measured 36 cycles for the probe, 43 for
       //      the issue-counter load, and neither overlaps the chain because both block the warp); larger groups take
       //      them from the ring.
+      const bool diag = stamps && blockIdx.x == 0;                     // diagnostics: cycles the chain waits for the helpers
+      long long t_chain_wait = 0;
       uint32_t c1 = 0, c2 = 0, c3 = 0;
       uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;                         // words b .. b+3 of row 32 b + lane
       bool have = false;                                               // d* hold block b's words
@@ -952,7 +1011,9 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       for (int b = 0; b < nhw; ++b) {
         if (b >= 4) {                                                  // every helper is done with the blocks <= b-4
           const uint32_t need = (uint32_t)(b - 3);
+          const long long tw = diag ? clock64() : 0;
           while (!__all_sync(0xffffffffu, lane >= kScanHelpers || ld_acquire_u32(&s_hprog[lane & 7]) >= need)) {}
+          if (diag) t_chain_wait += clock64() - tw;
         }
         const int rows_b = min(32, ng - 32 * b);
         uint32_t cur = ld_acquire_u32(&s_removed[b]) | c1;
@@ -978,16 +1039,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
           }
         }
         if (cur != ~0u) {                                              // a dead block needs neither its data nor a chain
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            const uint32_t da = __shfl_sync(0xffffffffu, d0, k), db = __shfl_sync(0xffffffffu, d0, k + 1);
-            // two decisions from the same `cur`: row k is kept iff its bit is clear; row k+1 iff its bit is clear in
-            // cur and, when row k is kept, also in row k's diagonal word
-            const bool ka = !(cur & (1u << k));
-            const bool kb = ka ? !((cur | da) & (2u << k)) : !(cur & (2u << k));
-            cur |= (ka ? da : 0u) | (kb ? db : 0u);
-            keep |= (ka ? (1u << k) : 0u) | (kb ? (2u << k) : 0u);
-          }
+          keep = greedy_block(cur, d0, lane);
           const bool kept = (keep >> lane) & 1u;
           n1 = __reduce_or_sync(0xffffffffu, kept ? d1 : 0u);
           n2 = __reduce_or_sync(0xffffffffu, kept ? d2 : 0u);
@@ -1000,20 +1052,26 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
         d0 = e0; d1 = e1; d2 = e2; d3 = e3; have = have_n;
         slot = slot_n; par = par_n;
       }
+      if (diag && lane == 0) { stamps[11] = t_chain_wait; stamps[12] = nhw; }
     } else {
       // ---- helpers: warp hw owns the words w = hw + kScanHelpers * i; lane (i % 32) keeps the accumulator of its i-th
       //      word in a register (two per lane cover nhw <= 256) and publishes it when the word's last block is done
       const int hw = warp - 2;
+      const bool diag = stamps && blockIdx.x == 0 && hw == 0;          // diagnostics: where helper warp 0 spends its cycles
+      long long t_k = 0, t_data = 0, t_work = 0;
       uint32_t acc0 = 0, acc1 = 0;
       for (int b = 0; b < nhw; ++b) {
+        long long t0 = diag ? clock64() : 0;
         mbar_wait(&bar_k[b % kScanSlotsMax], (b / kScanSlotsMax) & 1);
         const uint32_t keep = ld_acquire_u32(&s_keep[b]);
+        if (diag) { const long long t1 = clock64(); t_k += t1 - t0; t0 = t1; }
         if (keep && b + 4 < nhw) {
           const int slot = b % D;
           // the block's copy must have landed (in panel mode the chain never waits for the ring); the barrier counts for
           // this block only once the producer has armed it
           while (ld_acquire_u32(&s_issued) <= (uint32_t)b) {}
           mbar_wait(&bar_full[slot], (b / D) & 1);
+          if (diag) { const long long t1 = clock64(); t_data += t1 - t0; t0 = t1; }
           const uint32_t* blk = ring + slot * slot_words + lane - b * 32;
           const bool kept = (keep >> lane) & 1u;
           int i = (b + 4 - hw + kScanHelpers - 1) / kScanHelpers;      // first owned word >= b + 4
@@ -1038,7 +1096,9 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
         }
         __syncwarp();
         if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_hprog[hw])), "r"((uint32_t)(b + 1)) : "memory");
+        if (diag) t_work += clock64() - t0;
       }
+      if (diag && lane == 0) { stamps[8] = t_k; stamps[9] = t_data; stamps[10] = t_work; }
     }
     __syncthreads();
     for (int i = tid; i < ng; i += kFusedThreads)

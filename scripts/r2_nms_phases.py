@@ -46,7 +46,7 @@ def run(tag, boxes, scores, groups, thr, ng):
           + "  ".join("%s %.1f" % (a, b) for a, b in zip(NAMES, d)) + "  (us at 1965 MHz)")
     print("           key build of CTA 0: %.1f us" % ((st[13] - st[0]) / 1965.0))
     if st[12] > 0:
-        print("           helper warp 0, cycles per block over %d blocks: wait-keep %.0f  work %.0f  publish %.0f ; chain waiting for helpers %.0f"
+        print("           scan of CTA 0's group, cycles per block over %d blocks: helper warp 0 waits for the keep word %.0f, for the block's copy %.0f, works %.0f; the chain waits for the helpers %.0f"
               % (st[12], st[8] / st[12], st[9] / st[12], st[10] / st[12], st[11] / st[12]))
     if False:
         print("           chain of group 0, cycles per block over %d blocks: wait-helpers %.0f  wait-data %.0f  bits %.0f  publish %.0f"
