@@ -819,9 +819,9 @@ def run_ours(args, D):
         line["latency"] = {
             "c1": {"eager_us": c1_e, "graph_us": c1_g,
                    "workload": "C1: rotated IoU matrix 2000x2000 theta-OBB + single-class rotated NMS @0.1 of the 2000 boxes "
-                               "(6 kernels), no host read-back; back-to-back calls, L2 warm"},
+                               "(3 kernels: prologue + matrix + the fused NMS launch), no host read-back; back-to-back calls, L2 warm"},
             "c2": {"eager_us": c2_e, "graph_us": c2_g, "boxes": int(cb2.shape[0]),
-                   "workload": "C2: batched rotated NMS of the 15 classes (3 kernels), keep count left on the device"},
+                   "workload": "C2: batched rotated NMS of the 15 classes (one cooperative launch), keep count left on the device"},
             "how": "CUDA events around %d back-to-back calls; graph = one torch.cuda.CUDAGraph replayed as often" % (5 if args.quick else 200)}
 
     # the driver's record keeps the standard keys only: the other two quantities of the metric (NMS Mboxes/s, RoIAlign
