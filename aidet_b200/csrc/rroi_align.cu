@@ -781,6 +781,25 @@ rroi_tap_apply_kernel(const unsigned* __restrict__ ids, const float* __restrict_
 // few warps are done, which keeps the resident-warp count up although the tap count per pixel varies.
 constexpr int kGatherWarps = 1;
 
+// M taps of one pixel (M = 1..4, compile time): all loads issued before the first FMA, no predicates, no FMA for absent taps
+// (r1 ran every step as four predicated taps: at 2.6 merged taps per pixel a third of its FFMAs multiplied by zero).
+template <int M>
+__device__ __forceinline__ void gather_taps(const float4* __restrict__ grad_out, int nch, int cc, bool one, bool two, uint2 mine,
+                                            int rel, float4& a0, float4& a1) {
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 v[M], u[M]; float w[M];
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const unsigned row = __shfl_sync(0xffffffffu, mine.x, rel + i);
+    w[i] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, rel + i));
+    const float4* r = grad_out + (size_t)row * nch + cc;
+    v[i] = one ? __ldg(r) : zero;
+    u[i] = two ? __ldg(r + 32) : zero;
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) { a0 = vfma(w[i], v[i], a0); a1 = vfma(w[i], u[i], a1); }
+}
+
 template <int PX>
 __global__ void __launch_bounds__(kGatherWarps * 32, 26)
 rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restrict__ grad_out,
@@ -795,6 +814,11 @@ rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restric
   const unsigned run_begin = __shfl_sync(0xffffffffu, bnd_l, 0), run_end = __shfl_sync(0xffffffffu, bnd_l, np);
   const int nch = C >> 2;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // level of the warp's first pixel; its pixels are consecutive, so the level changes at most at lv.first[l0 + 1]
+  int l0 = 0;
+#pragma unroll
+  for (int q = 1; q < kMaxLevels; ++q) if (q < n_levels && p0 >= lv.first[q]) l0 = q;
+  const unsigned l0_end = lv.first[l0 + 1];
   for (int cb = 0; cb < nch; cb += 64) {            // every lane runs the loops: the shuffles need the full warp
     const int cc = cb + lane;
     const bool one = cc < nch, two = cc + 32 < nch;
@@ -804,9 +828,11 @@ rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restric
 #pragma unroll 1
     for (int j = 0; j < np; ++j) {
       const unsigned pix = p0 + j;
-      int l = 0;
+      int l = l0;
+      if (pix >= l0_end) {                          // rare: the warp's pixels straddle two levels
 #pragma unroll
-      for (int q = 1; q < kMaxLevels; ++q) if (q < n_levels && pix >= lv.first[q]) l = q;
+        for (int q = 1; q < kMaxLevels; ++q) if (q < n_levels && pix >= lv.first[q]) l = q;
+      }
       float4* dst = reinterpret_cast<float4*>(lv.grad[l]) + (size_t)(pix - lv.first[l]) * nch;
       float4 a0 = zero, a1 = zero;
       unsigned t = __shfl_sync(0xffffffffu, bnd_l, j);
@@ -818,21 +844,12 @@ rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restric
           if (chunk + lane < run_end) mine = __ldg(sorted + chunk + lane);
         }
         const int rel = (int)(t - chunk);
-        const int m = (int)min(min(4u, te - t), 32u - (unsigned)rel);
-        {                                           // up to 4 taps: all loads issued before the first FMA
-          float4 v[4], u[4]; float w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const unsigned row = __shfl_sync(0xffffffffu, mine.x, rel + i);
-            w[i] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, rel + i));
-            const float4* r = grad_out + (size_t)row * nch + cc;
-            const bool on = i < m;                   // warp uniform
-            v[i] = (on && one) ? __ldg(r) : zero;
-            u[i] = (on && two) ? __ldg(r + 32) : zero;
-            if (!on) w[i] = 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { a0 = vfma(w[i], v[i], a0); a1 = vfma(w[i], u[i], a1); }
+        const int m = (int)min(min(4u, te - t), 32u - (unsigned)rel);      // warp uniform
+        switch (m) {
+          case 1: gather_taps<1>(grad_out, nch, cc, one, two, mine, rel, a0, a1); break;
+          case 2: gather_taps<2>(grad_out, nch, cc, one, two, mine, rel, a0, a1); break;
+          case 3: gather_taps<3>(grad_out, nch, cc, one, two, mine, rel, a0, a1); break;
+          default: gather_taps<4>(grad_out, nch, cc, one, two, mine, rel, a0, a1); break;
         }
         t += (unsigned)m;
       }
