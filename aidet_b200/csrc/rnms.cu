@@ -251,10 +251,20 @@ __global__ void __launch_bounds__(256) nms_gather_kernel(const float* __restrict
   }
 }
 
+// units of a group with ng boxes: strips of 32 columns c = 0..ns-1, strip c needs rows 0 .. min(ng, 32c+32)-1 (every row
+// that precedes one of its columns, plus the rest of the diagonal block so that all of its words get written) in
+// chunks of RC rows: (c+1) * 32/RC units, the last strip ceil(ng / RC)
+__host__ __device__ __forceinline__ int fused_units(int ng, int q /* 32 / RC */, int rc) {
+  if (ng <= 0) return 0;
+  const int ns = (ng + 31) >> 5;
+  return q * ((ns - 1) * ns / 2) + (ng + rc - 1) / rc;
+}
+
 // tiles of tile_rows x 256 cols over the bounding rectangle of every group (tiles under the
 // diagonal are skipped by the mask kernel); prefix[g] = first tile id of group g.
+// unit_rc > 0: counts the warp-level mask units (fused_units with unit_rc rows per unit) instead of tiles.
 __global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __restrict__ gstart, const int* __restrict__ gend,
-                                                               int n_groups, int tile_rows, int* prefix) {
+                                                               int n_groups, int tile_rows, int* prefix, int unit_rc) {
   __shared__ int warp_sum[32];
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -262,7 +272,10 @@ __global__ void __launch_bounds__(1024) nms_tile_prefix_kernel(const int* __rest
   for (int base = 0; base < n_groups; base += 1024) {
     int g = base + threadIdx.x;
     int v = 0;
-    if (g < n_groups) { int ng = gend[g] - gstart[g]; v = ((ng + tile_rows - 1) / tile_rows) * ((ng + 255) / 256); }
+    if (g < n_groups) {
+      int ng = gend[g] - gstart[g];
+      v = unit_rc ? fused_units(ng, 32 / unit_rc, unit_rc) : ((ng + tile_rows - 1) / tile_rows) * ((ng + 255) / 256);
+    }
     int x = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
@@ -407,6 +420,92 @@ nms_mask_kernel(const typename O::Row* __restrict__ rows, const typename O::Col*
       }
     }
     __syncthreads();                                   // stage[buf] and desc[buf] are free again
+  }
+}
+
+// Many small groups (batched tiles, a scene's tile x class groups: a few hundred boxes each): 256-column tiles leave most
+// warps of a CTA without a strip above the diagonal (ncu on 120 groups of ~394 boxes: ~55 % of the warp slots idle at the
+// tile barrier, mask at 40 % of the roofline).  Here the work is the fused kernel's warp-level unit -- 32 columns (one
+// record per lane, in registers) x rc rows (warp-uniform loads), only units at or above the diagonal -- dealt round-robin
+// to all warps; no staging, no CTA barrier.  Row-major mask layout of the tile kernel (the scan kernel reads it).
+template <class O, bool GE>
+__global__ void __launch_bounds__(256, O::FMT == 8 ? 3 : 4)
+nms_mask_units_kernel(const typename O::Row* __restrict__ rows, const typename O::Col* __restrict__ cols,
+                      const int* __restrict__ gstart, const int* __restrict__ gend, const int* __restrict__ prefix,
+                      int n_groups, const float* __restrict__ thr, int n_thr, float one, int rc_rows,
+                      uint32_t* __restrict__ mask32, long long pitch32, int stage_prefix) {
+  using Row = typename O::Row;
+  extern __shared__ int sprefix_u[];                                   // [n_groups + 1] when stage_prefix
+  __shared__ __align__(16) Row wrows[8][32];                           // a warp's unit rows: ONE round trip per unit instead of one per row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (stage_prefix) {
+    for (int g = tid; g <= n_groups; g += 256) sprefix_u[g] = __ldg(prefix + g);
+    __syncthreads();
+    prefix = sprefix_u;
+  }
+  const int q = 32 / rc_rows;
+  const int total = prefix[n_groups];
+  const int u_step = gridDim.x * 8;
+  int cur_g = -1, cur_c = -1, start = 0, ng = 0;
+  typename O::Reg me; float area_me = 0.f, th = 0.f; bool zero_hit = false;
+  for (int u = blockIdx.x * 8 + warp; u < total; u += u_step) {
+    int lo = 0, hi = n_groups;                                         // last g with prefix[g] <= u
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= u) lo = mid; else hi = mid; }
+    const int g = lo;
+    if (g != cur_g) { start = __ldg(gstart + g); ng = __ldg(gend + g) - start; }
+    const int ns = (ng + 31) >> 5;
+    const int l = u - prefix[g];
+    int c = (int)((sqrtf(8.0f * (float)l / (float)q + 1.0f) - 1.0f) * 0.5f);   // strip: the largest c with q c (c+1) / 2 <= l
+    c = min(c, ns - 1);
+    while (c > 0 && q * (c * (c + 1) / 2) > l) --c;
+    while (c < ns - 1 && q * ((c + 1) * (c + 2) / 2) <= l) ++c;
+    const int r0 = (l - q * (c * (c + 1) / 2)) * rc_rows;
+    const int c0 = c << 5;
+    const int r_end = min(min(ng, c0 + 32), r0 + rc_rows);
+    const int j = c0 + lane;
+    const bool live = j < ng;
+    if (g != cur_g || c != cur_c) {
+      me = cols[start + (live ? j : ng - 1)];
+      area_me = O::area_c(me, one);
+      th = __ldg(thr + (n_thr == 1 ? 0 : g));
+      zero_hit = GE ? (0.0f >= th) : (0.0f > th);
+      cur_g = g; cur_c = c;
+    }
+    {                                                                  // the unit's rows are contiguous records: copy them as 16-byte pieces
+      constexpr int RQ = (int)sizeof(Row) / 16;
+      const float4* src = reinterpret_cast<const float4*>(rows + start + r0);
+      float4* dst = reinterpret_cast<float4*>(&wrows[warp][0]);
+      __syncwarp();                                                    // the previous unit's reads are done
+      for (int i = lane; i < (r_end - r0) * RQ; i += 32) dst[i] = __ldg(src + i);
+      __syncwarp();
+    }
+    const Row* rr = &wrows[warp][0] - r0;                              // rr[i] = row i of the group, r0 <= i < r_end
+    uint32_t word = 0;
+    bool dense = false;
+    if constexpr (!GE && O::FMT != 4)                                  // unit above the diagonal, every circle meets its first and last row
+      dense = r_end <= c0 && r_end > r0 && th >= 1e-4f &&
+              __all_sync(0xffffffffu, live && !O::disjoint(rr[r0], me) && !O::disjoint(rr[r_end - 1], me));
+    if (dense) {
+      if constexpr (!GE && O::FMT != 4) {
+        const float k1 = 1.0f + th, thb = th * area_me;
+#pragma unroll 2
+        for (int i = r0; i < r_end; ++i) {
+          const uint32_t bb = __ballot_sync(0xffffffffu, nms_hit_dense<O>(rr[i], me, area_me, one, th, k1, thb));
+          if (lane == (i & 31)) word = bb;
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int i = r0; i < r_end; ++i) {
+        const Row a = rr[i];                                           // warp-uniform address: one transaction
+        const bool hit = nms_hit<O, GE>(a, me, area_me, one, th, zero_hit);
+        const uint32_t bb = __ballot_sync(0xffffffffu, hit && live && j > i);
+        if (lane == (i & 31)) word = bb;
+      }
+    }
+    // rows r0 .. r_end-1 lie in one 32-row block (rc_rows divides 32): lane (i & 31) holds row i's word
+    const int i_mine = (r0 & ~31) + lane;
+    if (i_mine >= r0 && i_mine < r_end) mask32[(long long)(start + i_mine) * pitch32 + c] = word;
   }
 }
 
@@ -629,15 +728,6 @@ constexpr int kPanelBlocks = 64;           // groups of <= 64 blocks (2048 boxes
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v; asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v;
-}
-
-// units of a group with ng boxes: strips of 32 columns c = 0..ns-1, strip c needs rows 0 .. min(ng, 32c+32)-1 (every row
-// that precedes one of its columns, plus the rest of the diagonal block so that all of its words get written) in
-// chunks of RC rows: (c+1) * 32/RC units, the last strip ceil(ng / RC)
-__host__ __device__ __forceinline__ int fused_units(int ng, int q /* 32 / RC */, int rc) {
-  if (ng <= 0) return 0;
-  const int ns = (ng + 31) >> 5;
-  return q * ((ns - 1) * ns / 2) + (ng + rc - 1) / rc;
 }
 
 // key of box j inside its group: better boxes have smaller keys (score descending, then index ascending)
@@ -1272,7 +1362,24 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     while (tile_rows > 8 && est_tiles(tile_rows) < 8.0 * sms) tile_rows >>= 1;
   }
   const int local_prefix = (small && n_groups <= kLocalGroups) ? 1 : 0;
-  if (!local_prefix) nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix);
+  // groups of (on average) fewer than 2048 boxes: warp-level units instead of 256-column tiles (see nms_mask_units_kernel)
+  const bool units = !small && (long long)n < 2048LL * n_groups;
+  if (units) {
+    const int resident = sms * (O::FMT == 8 ? 3 : 4);
+    const int side = max(1, n / n_groups);
+    int rc_rows = 4;                                          // the finest split until there are >= 8 units per warp
+    while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= 8LL * resident * 8) rc_rows <<= 1;
+    nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix, rc_rows);
+    const int stage = n_groups <= 8192 ? 1 : 0;
+    const size_t psmem = stage ? (size_t)(n_groups + 1) * 4 : 0;
+    if (cmp == AIDET_CMP_GE)
+      nms_mask_units_kernel<O, true><<<resident, 256, psmem, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr, one,
+                                                                 rc_rows, mask32, L.pitch32, stage);
+    else
+      nms_mask_units_kernel<O, false><<<resident, 256, psmem, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr, one,
+                                                                  rc_rows, mask32, L.pitch32, stage);
+  } else {
+  if (!local_prefix) nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix, 0);
   {
     // upper bound of the tile count: every group padded to full tiles
     long long max_tiles = (long long)(ceil_div(n, tile_rows) + n_groups) * (ceil_div(n, kTileCols) + 1);
@@ -1283,6 +1390,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     else
       nms_mask_kernel<O, false><<<grid, kTileCols, 0, s>>>(rows, cols, gstart, gend, prefix, n_groups, thr, n_thr, one,
                                                            tile_rows, mask32, L.pitch32, counters, local_prefix);
+  }
   }
   const int removed_cap = ceil_div(ceil_div(n, 32), 4) * 4;          // any group may hold all n boxes
   const int scan_pw = min(kScanPWMax, max(32, ceil_div(ceil_div(n, 32), 32) * 32));
