@@ -240,7 +240,7 @@ def _nms_workspace(device, nbytes):
 
 
 def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_ge=False, plus_one=False, sync=True,
-                workspace=None):
+                workspace=None, keep_fill=None):
     """Batched greedy NMS.  boxes (n,4|5|8), scores (n,), group_ids (n,) int or None.
 
     iou_thr: float, or a (n_groups,) tensor / sequence of per-group thresholds.
@@ -249,6 +249,8 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
     n_groups and a float / tensor threshold so that nothing else touches the host).
     workspace: optional uint8 CUDA tensor of >= aidet_nms_workspace_bytes + 128 bytes owned by the caller; by default a
     cached per-(device, stream) buffer is reused, so a call allocates nothing but its two result tensors.
+    keep_fill: with sync=False, the value the entries of `keep` past n_keep hold (the kernels only write the first n_keep);
+    e.g. n, so that `mask = zeros(n + 1); mask[keep] = True` turns the result into a keep mask without reading n_keep.
     """
     fmt = boxes.size(-1)
     boxes = _f32c(boxes, fmt, "boxes")
@@ -280,7 +282,8 @@ def nms_batched(boxes, scores, group_ids=None, iou_thr=0.5, n_groups=None, cmp_g
         raise ValueError("iou_thr must be a scalar or have n_groups=%d entries" % n_groups)
     dev = device.index
     lib = L.lib()
-    keep = torch.empty((n,), dtype=torch.long, device=device)
+    keep = (torch.empty((n,), dtype=torch.long, device=device) if keep_fill is None
+            else torch.full((n,), int(keep_fill), dtype=torch.long, device=device))
     n_keep = torch.empty((1,), dtype=torch.int32, device=device)
     with torch.cuda.device(dev):
         ws_bytes = lib.aidet_nms_workspace_bytes(n, n_groups, fmt)
