@@ -526,6 +526,8 @@ def run_ours(args, D):
             # shard groups over ranks (independent units, no data-path collective)
             mine = (cg % G) == r if G > 1 else torch.ones_like(cg, dtype=torch.bool)
             cbd, csd, cgd = cb[mine].to(dev), cs[mine].to(dev), cg[mine].to(dev)
+            Fn.nms_batched(cbd, csd, cgd, 0.5, n_groups=ng)      # one-time costs (first cooperative launch of the process,
+            torch.cuda.synchronize(dev)                          # workspace growth) stay out of the device-time average
             L.prof_read(L.PROF_NMS_MASK, reset=True)
             ms, launches = timed(D, dev, args.steps, args.warmup,
                                  lambda: Fn.nms_batched(cbd, csd, cgd, 0.5, n_groups=ng), flush=flush)
@@ -548,6 +550,8 @@ def run_ours(args, D):
             if fmt8:
                 bb = synth.thetaobb2pointobb(bb).float()
             bbd, bsd = bb.to(dev), bs_.to(dev)
+            Fn.nms_batched(bbd, bsd, None, 0.5)
+            torch.cuda.synchronize(dev)
             L.prof_read(L.PROF_NMS_MASK, reset=True)
             ms, launches = timed(D, dev, args.steps, args.warmup, lambda: Fn.nms_batched(bbd, bsd, None, 0.5), flush=flush)
             k_ms, k_cnt = L.prof_read(L.PROF_NMS_MASK, reset=True)
