@@ -754,6 +754,8 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   int* const sprefix = reinterpret_cast<int*>(dyn);
   int* const sstart = sprefix + (n_groups + 2);
   int* const send = sstart + (n_groups + 2);
+  // phase 2 also stages each warp's unit rows there (8 warps x 32 records behind the tables, 128 B aligned)
+  Row* const wrows = reinterpret_cast<Row*>(dyn + (((size_t)(n_groups + 2) * 12 + 127) & ~(size_t)127));
   __shared__ int swarp[8];
   __shared__ __align__(8) uint64_t bar_full[kScanSlotsMax], bar_k[kScanSlotsMax];
   __shared__ uint32_t s_issued;              // blocks whose copy the producer has issued
@@ -967,12 +969,19 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
         zero_hit = GE ? (0.0f >= th) : (0.0f > th);
         cur_g = g; cur_c = c;
       }
-      const Row* rr = rows + start;
+      {                                                              // the unit's rows are contiguous records: ONE round trip,
+        constexpr int RQ = (int)sizeof(Row) / 16;                     // 16-byte pieces into the warp's slice of shared memory
+        const float4* src = reinterpret_cast<const float4*>(rows + start + r0);
+        float4* dst = reinterpret_cast<float4*>(wrows + warp * 32);
+        __syncwarp();                                                 // the previous unit's reads are done
+        for (int i = lane; i < (r_end - r0) * RQ; i += 32) dst[i] = __ldcg(src + i);
+        __syncwarp();
+      }
+      const Row* rr = wrows + warp * 32 - r0;                         // rr[i] = row i of the group, r0 <= i < r_end
       uint32_t word = 0;
 #pragma unroll 2
       for (int i = r0; i < r_end; ++i) {
-        const Row a = rr[i];                                          // warp-uniform address: one transaction, L1 hit after the first unit
-        const bool hit = nms_hit<O, GE>(a, me, area_me, one, th, zero_hit);
+        const bool hit = nms_hit<O, GE>(rr[i], me, area_me, one, th, zero_hit);
         const uint32_t bb = __ballot_sync(0xffffffffu, hit && live && j > i);
         if (lane == (i & 31)) word = bb;
       }
@@ -1311,7 +1320,8 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     // 48 KB (four CTAs per SM for the mask phase: per-image inputs hold many small groups, whose slots are tiny), smaller
     // ones -- possibly ONE group -- take up to 72 KB so that the helpers' ring runs several blocks ahead
     const int ring_words = (n > 32 * kPanelBlocks) ? max(2 * slot_max, 12288) : min(18432, 8 * slot_max + kPanelBlocks * 128);
-    const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12), (size_t)ring_words * 4);
+    const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12 + 128 + 8 * 32 * sizeof(Row)),
+                            (size_t)ring_words * 4);
     void* fn = (cmp == AIDET_CMP_GE) ? (void*)nms_fused_kernel<O, true> : (void*)nms_fused_kernel<O, false>;
     const int occ = fused_occupancy(fn, smem);
     if (occ > 0) {
