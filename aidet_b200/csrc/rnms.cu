@@ -979,11 +979,26 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       }
       const Row* rr = wrows + warp * 32 - r0;                         // rr[i] = row i of the group, r0 <= i < r_end
       uint32_t word = 0;
+      bool dense = false;
+      if constexpr (!GE && O::FMT != 4)                               // unit above the diagonal, every circle meets its first and last row
+        dense = r_end <= c0 && r_end > r0 && th >= 1e-4f &&
+                __all_sync(0xffffffffu, live && !O::disjoint(rr[r0], me) && !O::disjoint(rr[r_end - 1], me));
+      if (dense) {
+        if constexpr (!GE && O::FMT != 4) {
+          const float k1 = 1.0f + th, thb = th * area_me;
 #pragma unroll 2
-      for (int i = r0; i < r_end; ++i) {
-        const bool hit = nms_hit<O, GE>(rr[i], me, area_me, one, th, zero_hit);
-        const uint32_t bb = __ballot_sync(0xffffffffu, hit && live && j > i);
-        if (lane == (i & 31)) word = bb;
+          for (int i = r0; i < r_end; ++i) {
+            const uint32_t bb = __ballot_sync(0xffffffffu, nms_hit_dense<O>(rr[i], me, area_me, one, th, k1, thb));
+            if (lane == (i & 31)) word = bb;
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int i = r0; i < r_end; ++i) {
+          const bool hit = nms_hit<O, GE>(rr[i], me, area_me, one, th, zero_hit);
+          const uint32_t bb = __ballot_sync(0xffffffffu, hit && live && j > i);
+          if (lane == (i & 31)) word = bb;
+        }
       }
       // rows r0 .. r_end-1 live in one 32-row block (rc_rows divides 32): lane (i & 31) holds row i's word.
       // Blocked layout: word (block b, word c, row r) of the group at ((b * pitch32 + c) * 32 + r).
