@@ -800,8 +800,11 @@ __device__ __forceinline__ void gather_taps(const float4* __restrict__ grad_out,
   for (int i = 0; i < M; ++i) { a0 = vfma(w[i], v[i], a0); a1 = vfma(w[i], u[i], a1); }
 }
 
+#ifndef AIDET_ROI_GATHER_OCC
+#define AIDET_ROI_GATHER_OCC 26
+#endif
 template <int PX>
-__global__ void __launch_bounds__(kGatherWarps * 32, 26)
+__global__ void __launch_bounds__(kGatherWarps * 32, AIDET_ROI_GATHER_OCC)
 rroi_gather_kernel(GatherLevels lv, int n_levels, int C, const float4* __restrict__ grad_out,
                    const uint2* __restrict__ sorted, const unsigned* __restrict__ seg_begin) {
   const unsigned n_pix = lv.first[n_levels];

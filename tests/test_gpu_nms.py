@@ -61,6 +61,45 @@ def test_large_single_group(cuda, n, side, thr):
     print("n=%d side=%d: %d kept" % (n, side, kept))
 
 
+@pytest.mark.parametrize("fmt,cmp_ge", [(5, False), (8, False), (5, True), (4, True)])
+def test_many_small_groups_beyond_the_fused_kernel(cuda, fmt, cmp_ge):
+    """n > 8192 in groups of a few hundred boxes (batched tiles, a scene's tile x class groups): radix sort + the warp-level
+    mask units (nms_mask_units_kernel) + the scan kernel; ragged sizes, one empty group, per-group thresholds, ids outside
+    [0, n_groups) (never scanned, never kept) and keep_fill."""
+    from aidet_b200.ops import functional as F
+    n, ng = 12000, 40
+    boxes, scores = synth.dota_boxes(n, side=900, seed=61)
+    g = torch.Generator().manual_seed(5)
+    groups = torch.randint(0, ng - 1, (n,), generator=g).int()           # group ng-1 stays empty
+    groups[torch.randperm(n, generator=g)[:300]] = ng + 3                # not this call's share
+    thr = torch.linspace(0.2, 0.6, ng)
+    if fmt == 8:
+        boxes = synth.thetaobb2pointobb(boxes).float()
+    elif fmt == 4:
+        p = synth.thetaobb2pointobb(boxes).view(n, 4, 2)
+        boxes = torch.cat([p.min(1).values, p.max(1).values], 1).float()
+    keep, nk = F.nms_batched(boxes.to(cuda), scores.to(cuda), groups.to(cuda), thr.to(cuda), n_groups=ng, cmp_ge=cmp_ge,
+                             plus_one=(fmt == 4), sync=False, keep_fill=n)
+    k = int(nk)
+    assert (keep[k:] == n).all()
+    inds = keep[:k].cpu()
+    assert (inds[1:] > inds[:-1]).all() and (groups[inds] < ng).all()
+    ok = groups < ng
+    sel = ok.nonzero().flatten()
+    pos = torch.full((n,), -1, dtype=torch.long); pos[sel] = torch.arange(sel.numel())
+    ref_total = 0
+    for c in range(ng):                                                   # the oracle class by class (per-group thresholds)
+        m = (groups == c).nonzero().flatten()
+        if m.numel() == 0:
+            continue
+        got_c = inds[groups[inds] == c]
+        local = torch.searchsorted(m, got_c)
+        assert torch.equal(m[local], got_c)
+        kept, _ = _compare(boxes[m], scores[m], float(thr[c]), local.to(cuda), cmp_ge=cmp_ge, plus_one=(fmt == 4))
+        ref_total += kept
+    print("fmt %d ge %d: %d kept of %d" % (fmt, cmp_ge, k, int(ok.sum())))
+
+
 def test_pointobb_nms(cuda):
     boxes, scores = synth.dota_boxes(1200, side=512, seed=22)
     p8 = synth.thetaobb2pointobb(boxes)
