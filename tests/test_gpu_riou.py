@@ -116,12 +116,30 @@ def test_aligned_and_empty(cuda):
     assert tuple(rbbox_overlaps(e, e, is_aligned=True).shape) == (0, 1)
 
 
-def test_ragged_sizes(cuda):
-    """tile tails: sizes around the 256-column / 64-row tile edges."""
-    for m, n in [(1, 1), (63, 257), (65, 255), (130, 513), (1, 1000), (1000, 1)]:
-        a, _ = synth.dota_boxes(m, side=200, seed=20 + m)
-        b, _ = synth.dota_boxes(n, side=200, seed=40 + n)
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("fmt", [5, 8])
+def test_ragged_sizes(cuda, dense, fmt):
+    """tile tails: sizes around the 256-column / 64-row tile edges, odd row counts for the two-row steps; the dense sets
+    take the solid-tile loop (no per-pair circle test), the others the dual-row / early-out loops; both modes."""
+    for m, n in [(1, 1), (2, 3), (3, 256), (63, 257), (65, 255), (130, 513), (1, 1000), (1000, 1), (129, 1)]:
+        a, _ = synth.dota_boxes(m, side=200, seed=20 + m, dense=dense)
+        b, _ = synth.dota_boxes(n, side=200, seed=40 + n, dense=dense)
+        if fmt == 8:
+            a, b = synth.thetaobb2pointobb(a).float(), synth.thetaobb2pointobb(b).float()
         _check(a, b, cuda)
+        _check(a, b, cuda, mode="iof", tol=3e-5 if fmt == 8 else TOL)
+
+
+def test_solid_and_sparse_tiles_in_one_matrix(cuda):
+    """A column set that mixes a dense cluster with far-away boxes: warps of one tile take different loops (solid /
+    dual-row / early-out); far pairs must come out exactly 0 where the bounding circles are disjoint on the non-solid paths
+    and within tolerance everywhere."""
+    a, _ = synth.dota_boxes(700, side=16384, seed=71, dense=True)
+    b1, _ = synth.dota_boxes(512, side=16384, seed=72, dense=True)
+    b2, _ = synth.dota_boxes(700, side=16384, seed=73, dense=False)
+    b = torch.cat([b1[:256], b2[:300], b1[256:], b2[300:]])
+    got, ref = _check(a, b, cuda)
+    assert (got[:, 256:556][ref[:, 256:556] == 0] < 1e-6).all()
 
 
 def test_cpu_tensor_raises():
