@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(256) nms_keys_kernel(const float* __restrict__
 // w <= n_groups, the first position of group w (= #{key_j < w << 45}): gstart[w], and gend[w-1].  The prepared
 // record (geom.cuh) of every box goes straight to its sorted slot.
 constexpr int kRankSortMax = 8192;          // 13 index bits
+#ifndef AIDET_NMS_BUCKET_SORT
+#define AIDET_NMS_BUCKET_SORT 1             // n > kRankSortMax: bucket + rank kernels (1) or key kernel + CUB radix sort + gather (0)
+#endif
+constexpr bool kBucketSort = AIDET_NMS_BUCKET_SORT != 0;
 constexpr int kRankBoxes = 4;
 constexpr int kRankGroupShift = 45;         // 13 index + 32 score bits below the group
 constexpr int kRankMaxGroups = (1 << 19) - 2;
@@ -225,6 +229,148 @@ nms_rank_gather_kernel(const float* __restrict__ boxes, const float* __restrict_
       rows[rank] = r;
       if constexpr (!std::is_same<typename O::Row, typename O::Col>::value) cols[rank] = cc;
     }
+  }
+}
+
+// ------------------------------------------------------------------ 1b. bucket + rank (n > kRankSortMax)
+// The order NMS needs -- group ascending, score descending, original index ascending -- without a radix sort: a 64-bit
+// key sort of 16 k - 50 k elements is 4-5 latency-bound passes of ~10 us on three CTAs (59-69 us: a third of an 8-tile
+// batch).  Boxes are instead dealt to their group's bucket (counting sort by group id: histogram, scan, scatter -- warp
+// aggregated atomics, order inside a bucket arbitrary) and every box then ranks itself INSIDE its bucket by counting the
+// smaller keys (score bits, index): sum over groups of n_g^2 comparisons at ~0.12 warp instructions each -- 5 % of what the
+// mask kernel spends on the same dense group, ~60 % on a sparse one -- so the host keeps the radix sort for inputs whose
+// groups average more than 24576 boxes.
+__global__ void __launch_bounds__(256) nms_bucket_hist_kernel(const int* __restrict__ groups, int n, int n_groups,
+                                                              unsigned* __restrict__ gcnt, uint8_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[i] = 0;
+  const uint32_t g = groups ? min((uint32_t)__ldg(groups + i), (uint32_t)n_groups) : 0u;   // ids outside [0, n_groups): last bucket
+  const unsigned m = __match_any_sync(__activemask(), g);
+  if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(gcnt + g, (unsigned)__popc(m));
+}
+
+// exclusive scan of the n_groups + 1 bucket counts (one CTA): gbase[g] .. gbase[g + 1] = bucket g; cursors for the scatter;
+// group bounds of the n_groups real groups for the mask / scan kernels
+__global__ void __launch_bounds__(1024) nms_bucket_scan_kernel(unsigned* __restrict__ gcnt /* in: counts, out: gbase */,
+                                                               unsigned* __restrict__ gcursor, int n_groups,
+                                                               int* __restrict__ gstart, int* __restrict__ gend) {
+  __shared__ unsigned warp_sum[32];
+  __shared__ unsigned carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base <= n_groups; base += 1024) {
+    const int g = base + threadIdx.x;
+    const unsigned v = (g <= n_groups) ? gcnt[g] : 0u;
+    unsigned x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_sum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned incl = x + (warp ? warp_sum[warp - 1] : 0u) + carry;
+    if (g <= n_groups) {
+      const unsigned excl = incl - v;
+      gcnt[g] = excl; gcursor[g] = excl;
+      if (g < n_groups) { gstart[g] = (int)excl; gend[g] = (int)incl; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gcnt[n_groups + 1] = carry;           // = n: end of the last bucket
+}
+
+__global__ void __launch_bounds__(256) nms_bucket_scatter_kernel(const float* __restrict__ scores, const int* __restrict__ groups,
+                                                                 int n, int n_groups, unsigned* __restrict__ gcursor,
+                                                                 uint64_t* __restrict__ bkeys, int* __restrict__ bgrp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t g = groups ? min((uint32_t)__ldg(groups + i), (uint32_t)n_groups) : 0u;
+  const unsigned m = __match_any_sync(__activemask(), g);
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(gcursor + g, (unsigned)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  const unsigned pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+  bkeys[pos] = ((uint64_t)(~orderable(__ldg(scores + i))) << 32) | (uint64_t)(uint32_t)i;   // better boxes: smaller keys
+  bgrp[pos] = (int)g;
+}
+
+// A CTA owns 32 consecutive bucket positions (4 per warp).  The keys of the buckets those positions lie in -- one contiguous
+// range -- pass through shared memory in tiles; a box counts the keys of ITS bucket that are smaller than its own.  The
+// records are prepared by the first warp (consecutive lanes: rect_prepare evaluates sin / cos in double).
+constexpr int kBucketTile = 2048;
+template <class O>
+__global__ void __launch_bounds__(256) nms_bucket_rank_kernel(const float* __restrict__ boxes, const uint64_t* __restrict__ bkeys,
+                                                              const int* __restrict__ bgrp, const unsigned* __restrict__ gbase,
+                                                              int n, float one, typename O::Row* rows, typename O::Col* cols,
+                                                              int* __restrict__ order) {
+  __shared__ uint64_t tkeys[kBucketTile];
+  __shared__ int tgrp[kBucketTile];
+  __shared__ int s_pos[32], s_idx[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p_first = blockIdx.x * 32, p_last = min(n, p_first + 32) - 1;
+  const unsigned lo = gbase[__ldg(bgrp + p_first)], hi = gbase[__ldg(bgrp + p_last) + 1];   // union of the CTA's buckets
+  uint64_t ki[4]; int gi[4]; int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int p = p_first + warp * 4 + b;
+    ki[b] = (p < n) ? __ldg(bkeys + p) : 0ull;
+    gi[b] = (p < n) ? __ldg(bgrp + p) : -1;
+  }
+  const bool one_bucket = gi[0] == gi[3] || gi[3] < 0;        // the common case: no per-key group test
+  for (unsigned t0 = lo; t0 < hi; t0 += kBucketTile) {
+    const int tn = (int)min((unsigned)kBucketTile, hi - t0);
+    __syncthreads();
+    for (int j = tid; j < tn; j += 256) { tkeys[j] = __ldg(bkeys + t0 + j); tgrp[j] = __ldg(bgrp + t0 + j); }
+    __syncthreads();
+    if (gi[0] < 0) continue;
+    if (one_bucket && gi[0] == gi[1] && gi[0] == gi[2]) {
+      // the warp's boxes share a bucket: clip the tile to it once
+      const int j0 = max(0, (int)((long long)gbase[gi[0]] - (long long)t0)), j1 = min(tn, (int)((long long)gbase[gi[0] + 1] - (long long)t0));
+#pragma unroll 4
+      for (int j = j0 + lane; j < j1; j += 32) {
+        const uint64_t kj = tkeys[j];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cnt[b] += (kj < ki[b]) ? 1 : 0;
+      }
+    } else {
+      for (int j = lane; j < tn; j += 32) {
+        const uint64_t kj = tkeys[j]; const int gj = tgrp[j];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cnt[b] += (gj == gi[b] && kj < ki[b]) ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) cnt[b] = __reduce_add_sync(0xffffffffu, cnt[b]);
+  if (lane < 4) {
+    int c = cnt[0], g = gi[0]; uint64_t k = ki[0];
+#pragma unroll
+    for (int b = 1; b < 4; ++b) if (lane == b) { c = cnt[b]; g = gi[b]; k = ki[b]; }
+    s_pos[warp * 4 + lane] = (g >= 0) ? (int)gbase[g] + c : -1;
+    s_idx[warp * 4 + lane] = (int)(uint32_t)k;
+  }
+  __syncthreads();
+  if (tid < 32 && s_pos[tid] >= 0) {
+    const int pos = s_pos[tid], i = s_idx[tid];
+    order[pos] = i;
+    float bx[O::FMT];
+#pragma unroll
+    for (int k = 0; k < O::FMT; k++) bx[k] = __ldg(boxes + (size_t)i * O::FMT + k);
+    typename O::Row r; typename O::Col cc;
+    O::prepare(bx, one, &r, &cc);
+    rows[pos] = r;
+    if constexpr (!std::is_same<typename O::Row, typename O::Col>::value) cols[pos] = cc;
   }
 }
 
@@ -1256,7 +1402,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
 
 // ------------------------------------------------------------------ host side
 struct NmsLayout {
-  size_t keys_in, keys_out, idx_in, order, rows, cols, gbounds, prefix, flags, mask, cub, total;
+  size_t keys_in, keys_out, idx_in, order, rows, cols, gbounds, prefix, flags, mask, cub, gcnt, gcursor, total;
   long long pitch32;
   size_t cub_bytes;
 };
@@ -1279,6 +1425,7 @@ static NmsLayout nms_layout(int n, int n_groups, int fmt, size_t cub_bytes) {
   const size_t mask_rows = (size_t)n + ((n <= 8192 && n_groups <= 1024) ? 32 * (size_t)n_groups : 0);
   L.mask = take(mask_rows * (size_t)L.pitch32 * 4);
   L.cub_bytes = cub_bytes; L.cub = take(cub_bytes);
+  L.gcnt = take((size_t)(n_groups + 2) * 4); L.gcursor = take((size_t)(n_groups + 2) * 4);      // bucket counts / bases, cursors
   L.total = off + 384;                                       // the last 256 bytes: phase stamps of the fused kernel (diagnostics)
   return L;
 }
@@ -1369,12 +1516,24 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     nms_rank_gather_kernel<O><<<ceil_div(warps, kRankWarps), kRankWarps * 32, key_smem, s>>>(
         boxes, scores, groups, n, one, rows, cols, order, flags, gstart, gend, n_groups, counters);
   } else {
+    // rank-by-counting costs ~0.12 warp instructions per key pair inside a bucket: against the mask kernel's 0.19 (sparse
+    // groups, upper triangle) to 2.1 (dense) per pair it pays off while buckets stay below a few 10 k boxes; beyond that
+    // average size (one class of a whole scene) the radix sort's fixed ~70 us is cheaper
+    if (kBucketSort && (long long)n <= 24576LL * n_groups) {
+      unsigned* gcnt = (unsigned*)(ws + L.gcnt); unsigned* gcursor = (unsigned*)(ws + L.gcursor);
+      AIDET_CUDA(cudaMemsetAsync(gcnt, 0, (size_t)(n_groups + 2) * 4, s));
+      nms_bucket_hist_kernel<<<ceil_div(n, 256), 256, 0, s>>>(groups, n, n_groups, gcnt, flags);
+      nms_bucket_scan_kernel<<<1, 1024, 0, s>>>(gcnt, gcursor, n_groups, gstart, gend);
+      nms_bucket_scatter_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scores, groups, n, n_groups, gcursor, keys_in, idx_in);
+      nms_bucket_rank_kernel<O><<<ceil_div(n, 32), 256, 0, s>>>(boxes, keys_in, idx_in, gcnt, n, one, rows, cols, order);
+    } else {
     const int nb = ceil_div(max(n, 2 * n_groups), 256);
     nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
     size_t cub_bytes = L.cub_bytes;
     AIDET_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, idx_in, order, n, 0,
                                                32 + (groups ? group_bits(n_groups + 1) : 0), s));   // + 1: ids outside [0, n_groups) are clamped to n_groups and sort last
     nms_gather_kernel<O><<<ceil_div(n, 256), 256, 0, s>>>(boxes, keys_out, order, n, one, rows, cols, gstart, gend, n_groups);
+    }
   }
   const int sms = sm_count(device);
   // Row-tile height: the group sizes live on the device, so estimate the tile count as if the boxes were
