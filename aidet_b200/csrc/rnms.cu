@@ -312,20 +312,25 @@ constexpr int kBucketTile = 2048;
 template <class O>
 __global__ void __launch_bounds__(256) nms_bucket_rank_kernel(const float* __restrict__ boxes, const uint64_t* __restrict__ bkeys,
                                                               const int* __restrict__ bgrp, const unsigned* __restrict__ gbase,
-                                                              int n, float one, typename O::Row* rows, typename O::Col* cols,
-                                                              int* __restrict__ order) {
+                                                              int n, int n_groups, float one, typename O::Row* rows,
+                                                              typename O::Col* cols, int* __restrict__ order) {
   __shared__ uint64_t tkeys[kBucketTile];
   __shared__ int tgrp[kBucketTile];
   __shared__ int s_pos[32], s_idx[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int p_first = blockIdx.x * 32, p_last = min(n, p_first + 32) - 1;
-  const unsigned lo = gbase[__ldg(bgrp + p_first)], hi = gbase[__ldg(bgrp + p_last) + 1];   // union of the CTA's buckets
+  // the last bucket (ids outside [0, n_groups): never scanned, never kept) needs no order: its positions are skipped, and
+  // the CTA's key range ends at the last real bucket
+  const int g_first = __ldg(bgrp + p_first), g_last = min(__ldg(bgrp + p_last), n_groups - 1);
+  if (g_first >= n_groups) return;
+  const unsigned lo = gbase[g_first], hi = gbase[g_last + 1];                                // union of the CTA's buckets
   uint64_t ki[4]; int gi[4]; int cnt[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     const int p = p_first + warp * 4 + b;
     ki[b] = (p < n) ? __ldg(bkeys + p) : 0ull;
     gi[b] = (p < n) ? __ldg(bgrp + p) : -1;
+    if (gi[b] >= n_groups) gi[b] = -1;
   }
   const bool one_bucket = gi[0] == gi[3] || gi[3] < 0;        // the common case: no per-key group test
   for (unsigned t0 = lo; t0 < hi; t0 += kBucketTile) {
@@ -1525,7 +1530,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
       nms_bucket_hist_kernel<<<ceil_div(n, 256), 256, 0, s>>>(groups, n, n_groups, gcnt, flags);
       nms_bucket_scan_kernel<<<1, 1024, 0, s>>>(gcnt, gcursor, n_groups, gstart, gend);
       nms_bucket_scatter_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scores, groups, n, n_groups, gcursor, keys_in, idx_in);
-      nms_bucket_rank_kernel<O><<<ceil_div(n, 32), 256, 0, s>>>(boxes, keys_in, idx_in, gcnt, n, one, rows, cols, order);
+      nms_bucket_rank_kernel<O><<<ceil_div(n, 32), 256, 0, s>>>(boxes, keys_in, idx_in, gcnt, n, n_groups, one, rows, cols, order);
     } else {
     const int nb = ceil_div(max(n, 2 * n_groups), 256);
     nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
