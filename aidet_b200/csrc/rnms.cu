@@ -875,6 +875,10 @@ constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp u
 constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
 constexpr int kScanHelpers = kFusedThreads / 32 - 2;
 constexpr int kSoloBlocks = 16;           // groups of <= 16 blocks (512 boxes): scanned by one warp from shared memory
+#ifndef AIDET_NMS_SMALL_RING
+#define AIDET_NMS_SMALL_RING 18432     // ring words of problems of <= 2048 boxes (72 KB: two CTAs per SM in the mask phase)
+#endif
+constexpr int kSmallRing = AIDET_NMS_SMALL_RING;
 constexpr int kPanelBlocks = 64;           // groups of <= 64 blocks (2048 boxes): the chain's words live in a 32 KB panel
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -1486,7 +1490,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     // carved from its end).  Any group must get two ring slots; beyond that, problems of more than 2048 boxes stay at
     // 48 KB (four CTAs per SM for the mask phase: per-image inputs hold many small groups, whose slots are tiny), smaller
     // ones -- possibly ONE group -- take up to 72 KB so that the helpers' ring runs several blocks ahead
-    const int ring_words = (n > 32 * kPanelBlocks) ? max(2 * slot_max, 12288) : min(18432, 8 * slot_max + kPanelBlocks * 128);
+    const int ring_words = (n > 32 * kPanelBlocks) ? max(2 * slot_max, 12288) : min(kSmallRing, 12 * slot_max + kPanelBlocks * 128);
     const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12 + 128 + 8 * 32 * sizeof(Row)),
                             (size_t)ring_words * 4);
     void* fn = (cmp == AIDET_CMP_GE) ? (void*)nms_fused_kernel<O, true> : (void*)nms_fused_kernel<O, false>;
