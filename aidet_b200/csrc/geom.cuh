@@ -49,8 +49,9 @@ AIDET_HD float fdiv(float a, float b) { return a / b; }
 enum { MODE_IOU = 0, MODE_IOF = 1, MODE_IOF_B = 2 };
 
 // ---------------------------------------------------------------- records
-// theta-OBB, prepared once per box by the prologue kernel (32 B).  The same record serves
-// as "A" (the box that is transformed) and as "B" (the box whose frame is used).
+// theta-OBB, prepared once per box by the prologue kernel (32 B): the record of "B" (the box whose frame is used; a
+// kernel's column box).  "A" (the box that is transformed; a row box) is stored as RectA below (48 B: + reciprocal
+// edge lengths); callers that hold two Rects (aligned pairs, gradients) derive it per pair (rect_as_row).
 struct AIDET_ALIGN16 Rect {     // first 16 B: all the bounding-circle test needs (one LDS.128)
   float cx, cy;                  // centre
   float rad, area;               // circumradius (slightly inflated), w*h

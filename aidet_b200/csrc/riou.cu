@@ -5,9 +5,9 @@
 // (mmdet/datasets/dota.py:23,336).
 //
 // Layout / schedule:
-//   prologue  : one thread per box -> 32 B (theta-OBB) or 64 B (point-OBB) records in
-//               the caller's workspace: "row" records (the box that gets transformed)
-//               and "col" records (the box whose frame is used), see geom.cuh.
+//   prologue  : one thread per box -> records in the caller's workspace: "row" records (the box that
+//               gets transformed: 48 B RectA / 64 B QuadRow) and "col" records (the box whose frame is
+//               used: 32 B Rect / 64 B QuadCol), see geom.cuh.
 //   main      : persistent CTAs of 256 threads.  A tile is TR rows x 256 columns; each
 //               lane keeps ONE column record in registers and walks the row records,
 //               which a single thread stages into shared memory with a 1-D TMA bulk
@@ -15,10 +15,14 @@
 //               t+1 overlaps the arithmetic of tile t.  Row records are read from
 //               shared memory with warp-uniform 128-bit loads (broadcast); the result
 //               row segment of a warp is one 128 B coalesced streaming store.
-//               Per tile a two-row probe picks a dual-row loop (dense tiles: two clippings per
-//               step as one straight-line block) or the per-lane early-out loop (sparse tiles).
-//   bound     : FP32 issue (157 instructions per pair, 85 % of the issue slots; no tensor-core
-//               shape); output traffic 4 B/pair is ~1/8 of HBM peak at the achieved rate.
+//               Per tile a probe picks the loop: solid tiles (every lane's bounding circle meets the
+//               first two and the last row) run two clippings per step with no per-pair test, dense
+//               tiles the dual-row loop behind a warp vote, sparse tiles the per-lane early-out loop.
+//               Several destinations (row-sharded multi-GPU form): riou_matrix_tma_kernel, tiles leave
+//               through one TMA tensor store per destination GPU.
+//   bound     : FP32 issue (130 instructions per pair at 85 % of the issue slots: 240 Gpairs/s = 83 % of
+//               the 256-flop/pair roofline; no tensor-core shape); output traffic 4 B/pair is ~1/7 of HBM
+//               peak at that rate -- the DOTA-shaped (sparse) set IS bound by it (5 TB/s of stores).
 #include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
 #include <type_traits>

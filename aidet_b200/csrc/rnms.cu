@@ -5,18 +5,20 @@
 //   mmdet/ops/nms/src/nms_kernel.cu:71-139  device sort, D2H copy of the whole mask, serial host
 //                                           scan, H2D of keeps, cudaMalloc/Free per call
 //   mmdet/core/post_processing/rbbox_nms.py:29-49,83-106  Python loop over classes
-// with ONE device-side pass over all groups, no host round trip:
-//   1. keys    (group << 32 | ~orderable(score)), stable radix sort (CUB, the only library call)
-//              => order: group asc, score desc, original index asc on ties
-//   2. gather  sorted boxes -> prepared records (geom.cuh) + group [start,end)
-//   3. mask    upper-triangle suppression bitmask, 32-bit half-words = __ballot_sync of
-//              "IoU > thr" over 32 column boxes held in registers, row boxes staged by TMA
-//   4. scan    one CTA per group walks the rows in score order (greedy), entirely on device
-//   5. compact kept flags -> ascending original indices (nms_kernel.cu:135-138 semantics), done by
-//              whichever scan CTA finishes last
-// Up to 8192 boxes (every per-image config) steps 1-2 are ONE kernel (rank by counting) and the tile
-// prefix is computed inside the mask kernel: 3 launches per call.
-// Bound: step 3, FP32 issue (same pair arithmetic as riou.cu); steps 1,2,4,5 are latency.
+// with ONE device-side pass over all groups, no host round trip.
+// n <= 8192 boxes and <= 1024 groups (every per-image config): ONE cooperative launch, nms_fused_kernel:
+//   rank (keys in shared memory, rank by counting) -> mask (warp-level units) -> scan (one CTA per group) -> compaction.
+// Larger inputs:
+//   1. order   group asc, score desc, original index asc on ties: counting sort by group id (histogram, scan, scatter)
+//              + rank-by-counting inside each bucket; inputs whose groups average > 24576 boxes: 64-bit keys + CUB
+//              radix sort (the only library call) + gather.  Sorted boxes -> prepared records (geom.cuh), group bounds
+//   2. mask    upper-triangle suppression bitmask, 32-bit half-words = __ballot_sync of "IoU > thr" over 32 column
+//              boxes held in registers: 64 x 256 tiles handed out by a ticket counter with the row records staged by
+//              TMA, or warp-level units when the groups average < 2048 boxes
+//   3. scan    one CTA per group walks the rows in score order (greedy), entirely on device
+//   4. compact kept flags -> ascending original indices (nms_kernel.cu:135-138 semantics), done by whichever scan CTA
+//              finishes last
+// Bound: the mask, FP32 issue (same pair arithmetic as riou.cu); everything else is latency.
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 
