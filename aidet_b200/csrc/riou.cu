@@ -195,7 +195,10 @@ riou_matrix_kernel(const typename PairOp<K>::S* __restrict__ rows, int m,
 // at the matrix edge by the tensor map), local copy included.  The LSU issues no global store at all, the copy engine
 // streams full-size NVLink packets, and the stores of tile t overlap the arithmetic of tile t+1 (two tile buffers,
 // bulk-group commit / wait_group.read before a buffer is rewritten).
-constexpr int kTmaTileRows = 16;      // 16 KB tile buffers: four CTAs per SM like the single-destination kernel
+#ifndef AIDET_TMA_ROWS
+#define AIDET_TMA_ROWS 16
+#endif
+constexpr int kTmaTileRows = AIDET_TMA_ROWS;      // 16 rows: 16 KB tile buffers
 #ifndef AIDET_TMA_OBUFS
 #define AIDET_TMA_OBUFS 4             // tile buffers per CTA (stores in flight + 1); N = 2 on one box: 309 / 310 / 329 Gpairs/s with 2 / 3 / 4
 #endif
