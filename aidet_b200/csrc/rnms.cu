@@ -825,10 +825,17 @@ constexpr int kFusedCompactMax = 16384;
 __global__ void __launch_bounds__(1024) nms_compact_kernel(const uint8_t* __restrict__ flags, int n,
                                                            long long* __restrict__ keep_out, int* __restrict__ n_keep) {
   __shared__ int warp_sum[32];
-  const int per = (n + 1023) / 1024;
+  // each thread owns a run of `per` (multiple of 16) flags, read 16 at a time (the workspace slot is 128 B aligned and padded)
+  const int per = ((n + 1023) / 1024 + 15) & ~15;
   const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+  const uint4* f4 = reinterpret_cast<const uint4*>(flags);
   int cnt = 0;
-  for (int i = lo; i < hi; ++i) cnt += flags[i];
+  for (int i = lo; i < hi; i += 16) {
+    const uint4 v = __ldg(f4 + (i >> 4));
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) if (i + q < hi) cnt += (wds[q >> 2] >> (8 * (q & 3))) & 1u;
+  }
   int x = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
@@ -842,7 +849,13 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(const uint8_t* __rest
   }
   __syncthreads();
   int off = x - cnt + ((threadIdx.x >> 5) ? warp_sum[(threadIdx.x >> 5) - 1] : 0);
-  for (int i = lo; i < hi; ++i) if (flags[i]) keep_out[off++] = i;
+  for (int i = lo; i < hi; i += 16) {
+    const uint4 v = __ldg(f4 + (i >> 4));
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (i + q < hi && ((wds[q >> 2] >> (8 * (q & 3))) & 1u)) keep_out[off++] = i + q;
+  }
   if (threadIdx.x == 1023) *n_keep = off;
 }
 
