@@ -678,6 +678,9 @@ constexpr int kScanPWMax = 512;    // panel width in half-words, chosen per laun
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -689,7 +692,7 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
                                                        int* __restrict__ done) {
   extern __shared__ uint32_t sm[];
   uint32_t* removed = sm;                                   // [removed_cap]
-  uint32_t* panel = sm + removed_cap;                       // [2][32][kScanPW]
+  uint32_t* panel = sm + removed_cap;                       // [2][32][kScanPW + 4]
   __shared__ uint32_t keep_word;
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int start = gstart[g], ng = gend[g] - start;
@@ -702,14 +705,20 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
     if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);
     return cur == ~0u;
   };
+  // Panel rows hold the words from b & ~3 on (mask rows are 16-byte aligned: pitch32 is a multiple of 4), copied 16 bytes
+  // at a time -- a quarter of the cp.async instructions of a word-by-word copy; word b + w of row r is at
+  // [r * kPanelStride + (b & 3) + w].  The up to three words past the group's last one lie inside the row's pitch.
+  const int kPanelStride = kScanPW + 4;
   auto fetch = [&](int b, int buf) {
     const int pwn = min(kScanPW, nhw - b);
-    uint32_t* dst = panel + buf * (32 * kScanPW);
-    for (int idx = tid; idx < 32 * pwn; idx += 256) {
-      const int r = idx / pwn, w = idx - r * pwn;
+    const int b4 = b & ~3, nq = (pwn + (b & 3) + 3) >> 2;     // aligned first word, quads per row
+    uint32_t* dst = panel + buf * (32 * kPanelStride);
+    for (int idx = tid; idx < 32 * nq; idx += 256) {
+      const int r = idx / nq, q = idx - r * nq;
       const int row = b * 32 + r;
-      if (row < ng) cp_async4(dst + r * kScanPW + w, mask32 + (long long)(start + row) * pitch32 + b + w);
-      else dst[r * kScanPW + w] = 0u;
+      uint32_t* d4 = dst + r * kPanelStride + 4 * q;
+      if (row < ng) cp_async16(d4, mask32 + (long long)(start + row) * pitch32 + b4 + 4 * q);
+      else *reinterpret_cast<uint4*>(d4) = make_uint4(0u, 0u, 0u, 0u);
     }
     cp_async_commit();
   };
@@ -728,9 +737,9 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
     if (nb < nhw && !dead(nb)) { fetch(nb, buf ^ 1); pre = true; cp_async_wait<1>(); }   // speculative: b may still kill nb
     else cp_async_wait<0>();
     __syncthreads();                                        // panel[buf] landed
-    const uint32_t* pan = panel + buf * (32 * kScanPW);
+    const uint32_t* pan = panel + buf * (32 * kPanelStride) + (b & 3);     // word b + w of row r: pan[r * kPanelStride + w]
     if (tid < 32) {
-      const uint32_t d = pan[lane * kScanPW];               // diagonal half-word of row 32b + lane (0 past the end)
+      const uint32_t d = pan[lane * kPanelStride];          // diagonal half-word of row 32b + lane (0 past the end)
       uint32_t cur = removed[b];
       if (b == nhw - 1 && (ng & 31)) cur |= ~0u << (ng & 31);   // positions past the group end
       const uint32_t keep = greedy_block(cur, d, lane);
@@ -744,7 +753,7 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const uint32_t* __restric
     for (int idx = tid; idx < (pwn - 1) * 8; idx += 256) {
       const int w = 1 + (idx >> 3), part = idx & 7;
       uint32_t acc = 0, todo = (keep >> (part * 4)) & 0xfu;
-      while (todo) { const int k = part * 4 + __ffs(todo) - 1; todo &= todo - 1; acc |= pan[k * kScanPW + w]; }
+      while (todo) { const int k = part * 4 + __ffs(todo) - 1; todo &= todo - 1; acc |= pan[k * kPanelStride + w]; }
       if (acc) atomicOr(removed + b + w, acc);
     }
     for (int h = b + kScanPW + tid; h < nhw; h += 256) {    // beyond the panel: only for groups > 16384 boxes
@@ -1602,7 +1611,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
   }
   const int removed_cap = ceil_div(ceil_div(n, 32), 4) * 4;          // any group may hold all n boxes
   const int scan_pw = min(kScanPWMax, max(32, ceil_div(ceil_div(n, 32), 32) * 32));
-  const int sm_words = removed_cap + 2 * 32 * scan_pw;
+  const int sm_words = removed_cap + 2 * 32 * (scan_pw + 4);
   size_t scan_smem = (size_t)sm_words * 4;
   if (scan_smem > 48 * 1024) {
     if (scan_smem > 227 * 1024) { set_error("nms: %d boxes exceed the single-group scan capacity", n); return AIDET_EINVAL; }
