@@ -307,10 +307,12 @@ __global__ void __launch_bounds__(256) nms_bucket_scatter_kernel(const float* __
   bgrp[pos] = (int)g;
 }
 
-// A CTA owns 32 consecutive bucket positions (4 per warp).  The keys of the buckets those positions lie in -- one contiguous
+// A CTA owns 64 consecutive bucket positions (8 per warp).  The keys of the buckets those positions lie in -- one contiguous
 // range -- pass through shared memory in tiles; a box counts the keys of ITS bucket that are smaller than its own.  The
-// records are prepared by the first warp (consecutive lanes: rect_prepare evaluates sin / cos in double).
+// records are prepared by the first two warps (consecutive lanes: rect_prepare evaluates sin / cos in double).
 constexpr int kBucketTile = 2048;
+constexpr int kBucketPer = 8;                      // boxes per warp
+constexpr int kBucketCta = 8 * kBucketPer;         // positions per CTA
 template <class O>
 __global__ void __launch_bounds__(256) nms_bucket_rank_kernel(const float* __restrict__ boxes, const uint64_t* __restrict__ bkeys,
                                                               const int* __restrict__ bgrp, const unsigned* __restrict__ gbase,
@@ -318,57 +320,59 @@ __global__ void __launch_bounds__(256) nms_bucket_rank_kernel(const float* __res
                                                               typename O::Col* cols, int* __restrict__ order) {
   __shared__ uint64_t tkeys[kBucketTile];
   __shared__ int tgrp[kBucketTile];
-  __shared__ int s_pos[32], s_idx[32];
+  __shared__ int s_pos[kBucketCta], s_idx[kBucketCta];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int p_first = blockIdx.x * 32, p_last = min(n, p_first + 32) - 1;
+  const int p_first = blockIdx.x * kBucketCta, p_last = min(n, p_first + kBucketCta) - 1;
   // the last bucket (ids outside [0, n_groups): never scanned, never kept) needs no order: its positions are skipped, and
   // the CTA's key range ends at the last real bucket
   const int g_first = __ldg(bgrp + p_first), g_last = min(__ldg(bgrp + p_last), n_groups - 1);
   if (g_first >= n_groups) return;
   const unsigned lo = gbase[g_first], hi = gbase[g_last + 1];                                // union of the CTA's buckets
-  uint64_t ki[4]; int gi[4]; int cnt[4] = {0, 0, 0, 0};
+  const bool cta_one = g_first == g_last;          // every position of the CTA in one bucket (big buckets): no group ids needed
+  uint64_t ki[kBucketPer]; int gi[kBucketPer]; int cnt[kBucketPer];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    const int p = p_first + warp * 4 + b;
+  for (int b = 0; b < kBucketPer; ++b) {
+    const int p = p_first + warp * kBucketPer + b;
     ki[b] = (p < n) ? __ldg(bkeys + p) : 0ull;
     gi[b] = (p < n) ? __ldg(bgrp + p) : -1;
     if (gi[b] >= n_groups) gi[b] = -1;
+    cnt[b] = 0;
   }
-  const bool one_bucket = gi[0] == gi[3] || gi[3] < 0;        // the common case: no per-key group test
+  bool warp_one = gi[0] >= 0;                      // the warp's boxes share a bucket: clip the tile to it once
+#pragma unroll
+  for (int b = 1; b < kBucketPer; ++b) warp_one = warp_one && gi[b] == gi[0];
   for (unsigned t0 = lo; t0 < hi; t0 += kBucketTile) {
     const int tn = (int)min((unsigned)kBucketTile, hi - t0);
     __syncthreads();
-    for (int j = tid; j < tn; j += 256) { tkeys[j] = __ldg(bkeys + t0 + j); tgrp[j] = __ldg(bgrp + t0 + j); }
+    for (int j = tid; j < tn; j += 256) { tkeys[j] = __ldg(bkeys + t0 + j); if (!cta_one) tgrp[j] = __ldg(bgrp + t0 + j); }
     __syncthreads();
-    if (gi[0] < 0) continue;
-    if (one_bucket && gi[0] == gi[1] && gi[0] == gi[2]) {
-      // the warp's boxes share a bucket: clip the tile to it once
+    if (warp_one) {
       const int j0 = max(0, (int)((long long)gbase[gi[0]] - (long long)t0)), j1 = min(tn, (int)((long long)gbase[gi[0] + 1] - (long long)t0));
-#pragma unroll 4
+#pragma unroll 2
       for (int j = j0 + lane; j < j1; j += 32) {
         const uint64_t kj = tkeys[j];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) cnt[b] += (kj < ki[b]) ? 1 : 0;
+        for (int b = 0; b < kBucketPer; ++b) cnt[b] += (kj < ki[b]) ? 1 : 0;
       }
     } else {
       for (int j = lane; j < tn; j += 32) {
-        const uint64_t kj = tkeys[j]; const int gj = tgrp[j];
+        const uint64_t kj = tkeys[j]; const int gj = cta_one ? g_first : tgrp[j];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) cnt[b] += (gj == gi[b] && kj < ki[b]) ? 1 : 0;
+        for (int b = 0; b < kBucketPer; ++b) cnt[b] += (gj == gi[b] && kj < ki[b]) ? 1 : 0;
       }
     }
   }
 #pragma unroll
-  for (int b = 0; b < 4; ++b) cnt[b] = __reduce_add_sync(0xffffffffu, cnt[b]);
-  if (lane < 4) {
+  for (int b = 0; b < kBucketPer; ++b) cnt[b] = __reduce_add_sync(0xffffffffu, cnt[b]);
+  if (lane < kBucketPer) {
     int c = cnt[0], g = gi[0]; uint64_t k = ki[0];
 #pragma unroll
-    for (int b = 1; b < 4; ++b) if (lane == b) { c = cnt[b]; g = gi[b]; k = ki[b]; }
-    s_pos[warp * 4 + lane] = (g >= 0) ? (int)gbase[g] + c : -1;
-    s_idx[warp * 4 + lane] = (int)(uint32_t)k;
+    for (int b = 1; b < kBucketPer; ++b) if (lane == b) { c = cnt[b]; g = gi[b]; k = ki[b]; }
+    s_pos[warp * kBucketPer + lane] = (g >= 0) ? (int)gbase[g] + c : -1;
+    s_idx[warp * kBucketPer + lane] = (int)(uint32_t)k;
   }
   __syncthreads();
-  if (tid < 32 && s_pos[tid] >= 0) {
+  if (tid < kBucketCta && s_pos[tid] >= 0) {
     const int pos = s_pos[tid], i = s_idx[tid];
     order[pos] = i;
     float bx[O::FMT];
@@ -1558,7 +1562,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
       nms_bucket_hist_kernel<<<ceil_div(n, 256), 256, 0, s>>>(groups, n, n_groups, gcnt, flags);
       nms_bucket_scan_kernel<<<1, 1024, 0, s>>>(gcnt, gcursor, n_groups, gstart, gend);
       nms_bucket_scatter_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scores, groups, n, n_groups, gcursor, keys_in, idx_in);
-      nms_bucket_rank_kernel<O><<<ceil_div(n, 32), 256, 0, s>>>(boxes, keys_in, idx_in, gcnt, n, n_groups, one, rows, cols, order);
+      nms_bucket_rank_kernel<O><<<ceil_div(n, kBucketCta), 256, 0, s>>>(boxes, keys_in, idx_in, gcnt, n, n_groups, one, rows, cols, order);
     } else {
     const int nb = ceil_div(max(n, 2 * n_groups), 256);
     nms_keys_kernel<<<nb, 256, 0, s>>>(scores, groups, n, keys_in, idx_in, flags, gstart, n_groups);
