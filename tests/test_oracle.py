@@ -263,3 +263,47 @@ def test_float32_roialign_noise_floor():
     assert (err > 1e-4 * np.abs(hi)).mean() > 1e-3            # pure element-wise 1e-4 relative is not attainable in float32
     assert (err <= 1e-4 * np.abs(hi) + floor).all()           # the bound the GPU tests use holds for it
     assert err.max() > 0.02 * floor                           # and is not slack by orders of magnitude
+
+
+def test_greedy_block_fixed_point_equals_sequential_greedy():
+    """csrc/rnms.cu: greedy_block solves the 32 greedy decisions of a diagonal block by fixed-point iteration
+    K <- ~(init | OR_{j in K} D_j) over an upper-triangular bit matrix (D_j only holds bits > j).  Restated here in numpy
+    and compared with the sequential greedy loop on random, dense, empty and chain-shaped (worst case: 32 rounds) blocks."""
+    rng = np.random.default_rng(12)
+
+    def sequential(init, D):
+        cur, keep = int(init), 0
+        for k in range(32):
+            if not (cur >> k) & 1:
+                keep |= 1 << k
+                cur |= int(D[k])
+        return keep
+
+    def fixed_point(init, D):
+        K = ~int(init) & 0xffffffff
+        for rounds in range(1, 40):
+            R = int(init)
+            for j in range(32):
+                if (K >> j) & 1:
+                    R |= int(D[j])
+            Kn = ~R & 0xffffffff
+            if Kn == K:
+                return K, rounds
+            K = Kn
+        raise AssertionError("no fixed point within 39 rounds")
+
+    upper = np.array([(0xffffffff << (j + 1)) & 0xffffffff for j in range(32)], dtype=np.uint64)
+    cases = []
+    for density in (0.0, 0.02, 0.1, 0.5, 1.0):
+        for _ in range(400):
+            bits = rng.random((32, 32)) < density
+            D = np.array([sum(1 << c for c in range(32) if bits[j, c]) for j in range(32)], dtype=np.uint64) & upper
+            cases.append((int(rng.integers(0, 1 << 32)) if rng.random() < 0.5 else 0, D))
+    chain = np.array([(1 << (j + 1)) & 0xffffffff for j in range(32)], dtype=np.uint64)      # box j suppresses only box j + 1
+    cases.append((0, chain))
+    worst = 0
+    for init, D in cases:
+        keep, rounds = fixed_point(init, D)
+        assert keep == sequential(init, D)
+        worst = max(worst, rounds)
+    assert worst <= 33
