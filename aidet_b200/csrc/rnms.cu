@@ -903,6 +903,18 @@ constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp u
 constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
 constexpr int kScanHelpers = kFusedThreads / 32 - 2;
 constexpr int kSoloBlocks = 16;           // groups of <= 16 blocks (512 boxes): scanned by one warp from shared memory
+#ifndef AIDET_NMS_UNITS_PER_WARP
+#define AIDET_NMS_UNITS_PER_WARP 4      // fused kernel: mask units are split finer until each warp has this many
+#endif
+#ifndef AIDET_NMS_FUSED_MINB
+#define AIDET_NMS_FUSED_MINB 2          // fused kernel: resident CTAs per SM the register budget allows (128 registers)
+#endif
+#ifndef AIDET_NMS_FUSED_CTAS
+#define AIDET_NMS_FUSED_CTAS 2          // fused kernel: CTAs per SM (the grid barriers cost grows with the CTA count)
+#endif
+#ifndef AIDET_NMS_P1_WAVES
+#define AIDET_NMS_P1_WAVES 2            // CTAs per SM that take part in the fused kernel's ranking phase
+#endif
 #ifndef AIDET_NMS_SMALL_RING
 #define AIDET_NMS_SMALL_RING 18432     // ring words of problems of <= 2048 boxes (72 KB: two CTAs per SM in the mask phase)
 #endif
@@ -922,9 +934,11 @@ __device__ __forceinline__ int bucket_group(const int* __restrict__ groups, int 
   return (int)min(g, (uint32_t)n_groups);     // ids outside [0, n_groups) go to a bucket behind every group: never scanned
 }
 
-// 4 resident CTAs per SM (64 registers) for the 32-byte record kinds, 3 for the 64-byte quad records
+// 2 CTAs per SM with up to 128 registers: measured against 3 and 4 CTAs of 64 / 80 registers (round 3), the two grid
+// barriers cost 1.8 + 2.5 us with 296 CTAs against 3.5 + 5.5 us with 592, and the overlap arithmetic no longer spills;
+// config C2 went from 43 to 35 us per call, C1 from 74 to 66 us
 template <class O, bool GE>
-__global__ void __launch_bounds__(kFusedThreads, O::FMT == 8 ? 3 : 4)
+__global__ void __launch_bounds__(kFusedThreads, AIDET_NMS_FUSED_MINB)
 nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ groups,
                  int n, int n_groups, const float* __restrict__ thr, int n_thr, float one, int rc_rows,
                  typename O::Row* rows, typename O::Col* cols, int* order, uint8_t* flags, int* gstart, int* gend,
@@ -1119,7 +1133,9 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     // unit prefix over the groups; group starts / sizes / thresholds stay in shared memory (no L2 round trip per unit)
     for (int g = tid; g < n_groups; g += kFusedThreads) { sstart[g] = __ldcg(gstart + g); send[g] = __ldcg(gend + g); }
     __syncthreads();
+    stamp(14);
     cta_prefix([&](int g) { return fused_units(send[g] - sstart[g], q, rc_rows); }, n_groups);
+    stamp(15);
     const int total = sprefix[n_groups];
     // static, interleaved: run r = units 8r .. 8r+7 (one per warp: same strip as a rule, so the column record is
     // fetched from L2 once per CTA) goes to CTA r % grid -- neighbouring runs cost alike (same group, same place in the
@@ -1145,21 +1161,28 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       const int r_end = min(min(ng, c0 + 32), r0 + rc_rows);
       const int j = c0 + lane;
       const bool live = j < ng;
-      if (g != cur_g || c != cur_c) {
-        me = cols[start + (live ? j : ng - 1)];
-        area_me = O::area_c(me, one);
-        th = __ldg(thr + (n_thr == 1 ? 0 : g));
-        zero_hit = GE ? (0.0f >= th) : (0.0f > th);
-        cur_g = g; cur_c = c;
-      }
-      {                                                              // the unit's rows are contiguous records: ONE round trip,
-        constexpr int RQ = (int)sizeof(Row) / 16;                     // 16-byte pieces into the warp's slice of shared memory
-        const float4* src = reinterpret_cast<const float4*>(rows + start + r0);
-        float4* dst = reinterpret_cast<float4*>(wrows + warp * 32);
+      if (u < u_step) stamp(26);
+      {                                                              // the unit's rows are contiguous records: 16-byte
+        constexpr int RQ = (int)sizeof(Row) / 16;                     // pieces into the warp's slice of shared memory.  Their
+        const float4* src = reinterpret_cast<const float4*>(rows + start + r0);   // loads are issued BEFORE the column record's,
+        float4* dst = reinterpret_cast<float4*>(wrows + warp * 32);   // so a unit costs one L2 round trip, not two
+        const int pieces = (r_end - r0) * RQ;
+        float4 v[RQ];
+#pragma unroll
+        for (int k = 0; k < RQ; ++k) if (lane + 32 * k < pieces) v[k] = __ldcg(src + lane + 32 * k);
+        if (g != cur_g || c != cur_c) {
+          me = cols[start + (live ? j : ng - 1)];
+          th = __ldg(thr + (n_thr == 1 ? 0 : g));
+          area_me = O::area_c(me, one);
+          zero_hit = GE ? (0.0f >= th) : (0.0f > th);
+          cur_g = g; cur_c = c;
+        }
         __syncwarp();                                                 // the previous unit's reads are done
-        for (int i = lane; i < (r_end - r0) * RQ; i += 32) dst[i] = __ldcg(src + i);
+#pragma unroll
+        for (int k = 0; k < RQ; ++k) if (lane + 32 * k < pieces) dst[lane + 32 * k] = v[k];
         __syncwarp();
       }
+      if (u < u_step) stamp(27);
       const Row* rr = wrows + warp * 32 - r0;                         // rr[i] = row i of the group, r0 <= i < r_end
       uint32_t word = 0;
       bool dense = false;
@@ -1185,12 +1208,16 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       }
       // rows r0 .. r_end-1 live in one 32-row block (rc_rows divides 32): lane (i & 31) holds row i's word.
       // Blocked layout: word (block b, word c, row r) of the group at ((b * pitch32 + c) * 32 + r).
+      if (u < u_step) stamp(28);
       const int i_mine = (r0 & ~31) + lane;
       if (i_mine >= r0 && i_mine < r_end)
         mask32[(long long)(start + 32 * g) * pitch32 + ((long long)(r0 >> 5) * pitch32 + c) * 32 + lane] = word;
+      if (u < u_step) stamp(24);
       u += u_step;
     }
   }
+  stamp(25);
+  __syncthreads();
   stamp(3);
   grid.sync();
   stamp(4);
@@ -1516,7 +1543,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     const int slot_max = 32 * ((n + 31) >> 5);               // ring slot if all n boxes fall into one group
     // dynamic shared memory: all n keys (phase 1), later the scan's ring (+ the chain's panel for groups <= 2048 boxes,
     // carved from its end).  Any group must get two ring slots; beyond that, problems of more than 2048 boxes stay at
-    // 48 KB (four CTAs per SM for the mask phase: per-image inputs hold many small groups, whose slots are tiny), smaller
+    // 48 KB (per-image inputs hold many small groups, whose slots are tiny), smaller
     // ones -- possibly ONE group -- take up to 72 KB so that the helpers' ring runs several blocks ahead
     const int ring_words = (n > 32 * kPanelBlocks) ? max(2 * slot_max, 12288) : min(kSmallRing, 12 * slot_max + kPanelBlocks * 128);
     const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12 + 128 + 8 * 32 * sizeof(Row)),
@@ -1525,13 +1552,13 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     const int occ = fused_occupancy(fn, smem);
     if (occ > 0) {
       const int sms = sm_count(device);
-      const int grid = sms * min(occ, 4);
+      const int grid = sms * min(occ, AIDET_NMS_FUSED_CTAS);
       const int n_gwarps = grid * (kFusedThreads / 32);
       // rows per mask unit: the finest split until there are >= 8 units per warp (estimated for evenly filled groups)
       const int side = max(1, n / n_groups);
       int rc_rows = 4;
-      while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= 8LL * n_gwarps) rc_rows <<= 1;
-      int nn = n, ng_ = n_groups, nthr = n_thr, rwords = ring_words, p1 = min(grid, sms);
+      while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= (long long)AIDET_NMS_UNITS_PER_WARP * n_gwarps) rc_rows <<= 1;
+      int nn = n, ng_ = n_groups, nthr = n_thr, rwords = ring_words, p1 = min(grid, sms * AIDET_NMS_P1_WAVES);
       long long pitch = L.pitch32;
       int* done = counters + 1;
       int* ticket = counters;

@@ -45,6 +45,10 @@ def run(tag, boxes, scores, groups, thr, ng):
     print("%-10s n=%5d groups=%3d kept=%5d  call %.1f us | " % (tag, n, ng, int(nk), e0.elapsed_time(e1) * 20)
           + "  ".join("%s %.1f" % (a, b) for a, b in zip(NAMES, d)) + "  (us at 1965 MHz)")
     print("           key build of CTA 0: %.1f us" % ((st[13] - st[0]) / 1965.0))
+    print("           mask phase of CTA 0: bounds %.1f  unit prefix %.1f  first unit of warp 0 %.1f  warp 0 done %.1f  all warps %.1f us"
+          % tuple((st[b] - st[a]) / 1965.0 for a, b in ((2, 14), (14, 15), (15, 24), (24, 25), (25, 3))))
+    print("           first unit of warp 0: index math %.2f  loads %.2f  rows %.2f  store %.2f us"
+          % tuple((st[b] - st[a]) / 1965.0 for a, b in ((15, 26), (26, 27), (27, 28), (28, 24))))
     if st[12] > 0:
         print("           scan of CTA 0's group, cycles per block over %d blocks: helper warp 0 waits for the keep word %.0f, for the block's copy %.0f, works %.0f; the chain waits for the helpers %.0f"
               % (st[12], st[8] / st[12], st[9] / st[12], st[10] / st[12], st[11] / st[12]))
