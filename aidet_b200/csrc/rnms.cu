@@ -898,7 +898,13 @@ namespace cg = cooperative_groups;
 
 constexpr int kFusedMaxBoxes = 8192;
 constexpr int kFusedMaxGroups = 1024;
-constexpr int kFusedThreads = 256;
+#ifndef AIDET_NMS_PRODUCER_SLEEP
+#define AIDET_NMS_PRODUCER_SLEEP __nanosleep(64)
+#endif
+#ifndef AIDET_NMS_FUSED_THREADS
+#define AIDET_NMS_FUSED_THREADS 256
+#endif
+constexpr int kFusedThreads = AIDET_NMS_FUSED_THREADS;
 constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp unit
 constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
 constexpr int kScanHelpers = kFusedThreads / 32 - 2;
@@ -953,11 +959,12 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   int* const send = sstart + (n_groups + 2);
   // phase 2 also stages each warp's unit rows there (8 warps x 32 records behind the tables, 128 B aligned)
   Row* const wrows = reinterpret_cast<Row*>(dyn + (((size_t)(n_groups + 2) * 12 + 127) & ~(size_t)127));
-  __shared__ int swarp[8];
+  __shared__ int swarp[kFusedThreads / 32];
   __shared__ __align__(8) uint64_t bar_full[kScanSlotsMax], bar_k[kScanSlotsMax];
   __shared__ uint32_t s_issued;              // blocks whose copy the producer has issued
-  __shared__ uint32_t s_hprog[8];            // blocks finished by each helper warp (written by its lane 0 only)
-  __shared__ uint32_t s_keep[kFusedMaxBoxes / 32], s_removed[kFusedMaxBoxes / 32];
+  __shared__ uint32_t s_hprog[kFusedThreads / 32];            // blocks finished by each helper warp (written by its lane 0 only)
+  __shared__ uint32_t s_keep[kFusedMaxBoxes / 32];
+  __shared__ unsigned long long s_rem64[kFusedMaxBoxes / 32];   // (block + 1) << 32 | removed bits of the block, ONE 8-byte store
   __shared__ int s_last;
   cg::grid_group grid = cg::this_grid();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1279,9 +1286,9 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       continue;
     }
     if (tid < kScanSlotsMax) { mbar_init(&bar_full[tid], 1); mbar_init(&bar_k[tid], 1); fence_barrier_init(); }
-    for (int h = tid; h < nhw; h += kFusedThreads) { s_removed[h] = 0u; s_keep[h] = 0u; }
-    if (tid < 8) s_hprog[tid] = 0u;
-    if (tid == 8) s_issued = 0u;
+    for (int h = tid; h < nhw; h += kFusedThreads) { s_keep[h] = 0u; s_rem64[h] = 0ull; }
+    if (tid < kWarps) s_hprog[tid] = 0u;
+    if (tid == kWarps) s_issued = 0u;
     if (use_panel) {
       // block b: its words b .. b+3 are 128 consecutive words of the blocked layout -> one 16-byte load per lane
 #pragma unroll 8
@@ -1294,20 +1301,29 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     __syncthreads();
     if (warp == 1) {
       // ---- producer: block b = words b .. nhw-1 of rows 32b .. 32b+31, contiguous in the blocked layout
-      if (lane == 0) {
-        for (int b = 0; b < nhw; ++b) {
-          const int slot = b % D;
+      //      (panel mode needs no ring: the chain reads the panel, the helpers stream their words from L2)
+      if (lane == 0 && !use_panel) {
+        const bool pdiag = stamps && blockIdx.x == 0;
+        long long tp_h = 0, tp_l = 0, p_sleeps = 0;
+        const long long tp_begin = pdiag ? clock64() : 0;
+        int slot = 0; uint32_t par_prev = 1;                           // b % D and ((b - D) / D) & 1 without a division per block
+        for (int b = 0; b < nhw; ++b, ++slot) {
+          if (slot == D) { slot = 0; par_prev ^= 1u; }
           if (b >= D) {                                                // every helper warp is done with block b - D
             const uint32_t need = (uint32_t)(b - D + 1);
+            const long long tp0 = pdiag ? clock64() : 0;
             for (int h = 0; h < kScanHelpers; ++h)
-              while (ld_acquire_u32(&s_hprog[h]) < need) __nanosleep(64);
-            mbar_wait(&bar_full[slot], ((b - D) / D) & 1);             // its copy has landed (the chain skips that wait on dead blocks)
+              while (ld_acquire_u32(&s_hprog[h]) < need) { AIDET_NMS_PRODUCER_SLEEP; ++p_sleeps; }
+            const long long tp1 = pdiag ? clock64() : 0;
+            mbar_wait(&bar_full[slot], par_prev);                      // its copy has landed (the chain skips that wait on dead blocks)
+            if (pdiag) { tp_h += tp1 - tp0; tp_l += clock64() - tp1; }
           }
           const uint32_t bytes = (uint32_t)((nhw - b) * 128);
           mbar_expect_tx(&bar_full[slot], bytes);
           tma_load_1d(ring + slot * slot_words, mgrp + ((long long)b * pitch32 + b) * 32, bytes, &bar_full[slot]);
           asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_issued)), "r"((uint32_t)(b + 1)) : "memory");
         }
+        if (pdiag) { stamps[24] = tp_h; stamps[25] = tp_l; stamps[26] = p_sleeps; stamps[27] = clock64() - tp_begin; stamps[28] = D; }
       }
     } else if (warp == 0) {
       // ---- chain.  Per block: removed bits of its 32 rows (helpers: blocks <= b-4; own carries: blocks b-3..b-1) ->
@@ -1333,14 +1349,19 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       };
       if (use_panel) { fetch(0, panel + lane, d0, d1, d2, d3); have = true; }
       for (int b = 0; b < nhw; ++b) {
-        if (b >= 4) {                                                  // every helper is done with the blocks <= b-4
-          const uint32_t need = (uint32_t)(b - 3);
+        uint32_t cur = c1;
+        if (b >= 4) {
           const long long tw = diag ? clock64() : 0;
-          while (!__all_sync(0xffffffffu, lane >= kScanHelpers || ld_acquire_u32(&s_hprog[lane & 7]) >= need)) {}
+          // the word's owner publishes it, stamped with its block, in one 8-byte store once the blocks <= b-4 are in:
+          // no flag next to the data, so no fence on the helper's side and no wait for the OTHER helpers
+          unsigned long long v;
+          do {
+            asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(&s_rem64[b])) : "memory");
+          } while ((uint32_t)(v >> 32) != (uint32_t)(b + 1));
+          cur |= (uint32_t)v;
           if (diag) t_chain_wait += clock64() - tw;
         }
         const int rows_b = min(32, ng - 32 * b);
-        uint32_t cur = ld_acquire_u32(&s_removed[b]) | c1;
         if (rows_b < 32) cur |= ~0u << rows_b;
         int slot_n = slot + 1; uint32_t par_n = par;
         if (slot_n == D) { slot_n = 0; par_n ^= 1u; }
@@ -1382,19 +1403,67 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
       //      word in a register (two per lane cover nhw <= 256) and publishes it when the word's last block is done
       const int hw = warp - 2;
       const bool diag = stamps && blockIdx.x == 0 && hw == 0;          // diagnostics: where helper warp 0 spends its cycles
-      long long t_k = 0, t_data = 0, t_work = 0;
-      uint32_t acc0 = 0, acc1 = 0;
-      for (int b = 0; b < nhw; ++b) {
+      long long t_k = 0, t_data = 0, t_work = 0, t_iss = 0, t_iss_max = 0; int b_iss_max = 0, n_iss_slow = 0;
+      uint32_t acc0 = 0, acc1 = 0, issued = 0;
+      if (use_panel) {
+        // groups of <= 2048 boxes: no ring, no producer, no issue counter.  The 192 helper lanes pair up, a pair per word
+        // (words 4 .. 63): a lane keeps 16 of the 32 rows of ITS word for the next two blocks in registers (64 contiguous
+        // bytes of the blocked layout, four 16-byte loads straight from L2), ANDs them with the keep bits as soon as
+        // the chain publishes those, folds the pair with one shuffle and ORs the result into the word's accumulator; the
+        // pair's first lane publishes word b + 4 after block b, stamped, in one 8-byte store.  (Measured at config C1: the
+        // ring form spent ~900 cycles per block on the helper side -- redux.or per word, two integer divisions for the
+        // slot, the issue counter -- and the chain waited ~450 of its ~1190 cycles per block for it.)
+        const int gl = hw * 32 + lane, w = gl >> 1, half = gl & 1;
+        uint4 cur[4], nxt[4], nx2[4];
+        auto load = [&](int b, uint4 (&v)[4]) {
+          const bool on = w >= b + 4 && w < nhw && b < nhw;
+          const uint4* src = reinterpret_cast<const uint4*>(mgrp + ((long long)b * pitch32 + w) * 32 + half * 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = on ? __ldcg(src + k) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        load(0, nxt);
+        load(1, nx2);
+        for (int b = 0; b < nhw; ++b) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { cur[k] = nxt[k]; nxt[k] = nx2[k]; }
+          load(b + 2, nx2);
+          long long t0 = diag ? clock64() : 0;
+          mbar_wait(&bar_k[b % kScanSlotsMax], (b / kScanSlotsMax) & 1);
+          const uint32_t keep = ld_acquire_u32(&s_keep[b]);
+          if (diag) { const long long t1 = clock64(); t_k += t1 - t0; t0 = t1; }
+          if (keep && b + 4 < nhw) {
+            const uint32_t kk = keep >> (half * 16);
+            uint32_t m = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              m |= ((kk >> (4 * k)) & 1u) ? cur[k].x : 0u;
+              m |= ((kk >> (4 * k + 1)) & 1u) ? cur[k].y : 0u;
+              m |= ((kk >> (4 * k + 2)) & 1u) ? cur[k].z : 0u;
+              m |= ((kk >> (4 * k + 3)) & 1u) ? cur[k].w : 0u;
+            }
+            m |= __shfl_xor_sync(0xffffffffu, m, 1);
+            acc0 |= m;
+          }
+          if (w == b + 4 && w < nhw && half == 0) {
+            const unsigned long long v = ((unsigned long long)(uint32_t)(w + 1) << 32) | acc0;
+            asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(&s_rem64[w])), "l"(v) : "memory");
+          }
+          if (diag) t_work += clock64() - t0;
+        }
+      } else {
+      int slot = 0; uint32_t par = 0;                                  // b % D, (b / D) & 1 without a division per block
+      for (int b = 0; b < nhw; ++b, ++slot) {
+        if (slot == D) { slot = 0; par ^= 1u; }
         long long t0 = diag ? clock64() : 0;
         mbar_wait(&bar_k[b % kScanSlotsMax], (b / kScanSlotsMax) & 1);
         const uint32_t keep = ld_acquire_u32(&s_keep[b]);
         if (diag) { const long long t1 = clock64(); t_k += t1 - t0; t0 = t1; }
         if (keep && b + 4 < nhw) {
-          const int slot = b % D;
           // the block's copy must have landed (in panel mode the chain never waits for the ring); the barrier counts for
           // this block only once the producer has armed it
-          while (ld_acquire_u32(&s_issued) <= (uint32_t)b) {}
-          mbar_wait(&bar_full[slot], (b / D) & 1);
+          while (issued <= (uint32_t)b) issued = ld_acquire_u32(&s_issued);   // cached: the producer runs blocks ahead
+          if (diag) { const long long t1 = clock64(); t_iss += t1 - t0; if (t1 - t0 > t_iss_max) { t_iss_max = t1 - t0; b_iss_max = b; } n_iss_slow += (t1 - t0 > 200); }
+          mbar_wait(&bar_full[slot], par);
           if (diag) { const long long t1 = clock64(); t_data += t1 - t0; t0 = t1; }
           const uint32_t* blk = ring + slot * slot_words + lane - b * 32;
           const bool kept = (keep >> lane) & 1u;
@@ -1416,13 +1485,17 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
         const int wf = b + 4;
         if (wf < nhw && wf % kScanHelpers == hw) {
           const int i = wf / kScanHelpers;
-          if (lane == (i & 31)) s_removed[wf] = (i < 32) ? acc0 : acc1;
+          if (lane == (i & 31)) {
+            const unsigned long long v = ((unsigned long long)(uint32_t)(wf + 1) << 32) | ((i < 32) ? acc0 : acc1);
+            asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(&s_rem64[wf])), "l"(v) : "memory");
+          }
         }
         __syncwarp();
         if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_hprog[hw])), "r"((uint32_t)(b + 1)) : "memory");
         if (diag) t_work += clock64() - t0;
       }
-      if (diag && lane == 0) { stamps[8] = t_k; stamps[9] = t_data; stamps[10] = t_work; }
+      }
+      if (diag && lane == 0) { stamps[8] = t_k; stamps[9] = t_data; stamps[10] = t_work; stamps[29] = t_iss; stamps[30] = t_iss_max; stamps[31] = b_iss_max * 1000 + n_iss_slow; }
     }
     __syncthreads();
     for (int i = tid; i < ng; i += kFusedThreads)
@@ -1546,7 +1619,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     // 48 KB (per-image inputs hold many small groups, whose slots are tiny), smaller
     // ones -- possibly ONE group -- take up to 72 KB so that the helpers' ring runs several blocks ahead
     const int ring_words = (n > 32 * kPanelBlocks) ? max(2 * slot_max, 12288) : min(kSmallRing, 12 * slot_max + kPanelBlocks * 128);
-    const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12 + 128 + 8 * 32 * sizeof(Row)),
+    const size_t smem = max(max((size_t)n * 8 + (size_t)(n_groups + 1) * 8, (size_t)(n_groups + 2) * 12 + 128 + (kFusedThreads / 32) * 32 * sizeof(Row)),
                             (size_t)ring_words * 4);
     void* fn = (cmp == AIDET_CMP_GE) ? (void*)nms_fused_kernel<O, true> : (void*)nms_fused_kernel<O, false>;
     const int occ = fused_occupancy(fn, smem);

@@ -50,8 +50,10 @@ def run(tag, boxes, scores, groups, thr, ng):
     print("           first unit of warp 0: index math %.2f  loads %.2f  rows %.2f  store %.2f us"
           % tuple((st[b] - st[a]) / 1965.0 for a, b in ((15, 26), (26, 27), (27, 28), (28, 24))))
     if st[12] > 0:
-        print("           scan of CTA 0's group, cycles per block over %d blocks: helper warp 0 waits for the keep word %.0f, for the block's copy %.0f, works %.0f; the chain waits for the helpers %.0f"
-              % (st[12], st[8] / st[12], st[9] / st[12], st[10] / st[12], st[11] / st[12]))
+        print("           scan of CTA 0's group, cycles per block over %d blocks: helper warp 0 waits for the keep word %.0f, for the block's copy %.0f (of which until the producer has issued it %.0f), works %.0f; the chain waits for the helpers %.0f"
+              % (st[12], st[8] / st[12], st[9] / st[12], st[29] / st[12], st[10] / st[12], st[11] / st[12]))
+        print("           longest wait for an issue: %d cycles at block %d; %d blocks waited > 200 cycles" % (st[30], st[31] // 1000, st[31] % 1000))
+        print("           producer: %d cycles in all, %d waiting for helpers (%d sleeps), %d for landings, D = %d" % (st[27], st[24], st[26], st[25], st[28]))
     if False:
         print("           chain of group 0, cycles per block over %d blocks: wait-helpers %.0f  wait-data %.0f  bits %.0f  publish %.0f"
               % (st[12], st[8] / st[12], st[9] / st[12], st[10] / st[12], st[11] / st[12]))
