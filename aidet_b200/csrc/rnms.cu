@@ -29,6 +29,10 @@
 #include "common.cuh"
 #include "geom.cuh"
 
+#ifndef AIDET_NMS_COMPACT_PAIRS
+#define AIDET_NMS_COMPACT_PAIRS 1          // sparse mask units: lanes walk their own circle-test candidates
+#endif
+
 namespace aidet {
 
 // ------------------------------------------------------------------ box kinds
@@ -594,6 +598,7 @@ nms_mask_units_kernel(const typename O::Row* __restrict__ rows, const typename O
   using Row = typename O::Row;
   extern __shared__ int sprefix_u[];                                   // [n_groups + 1] when stage_prefix
   __shared__ __align__(16) Row wrows[8][32];                           // a warp's unit rows: ONE round trip per unit instead of one per row
+  __shared__ uint32_t s_ww[8][32];                                     // a warp's row words while its lanes walk their own candidates
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (stage_prefix) {
     for (int g = tid; g <= n_groups; g += 256) sprefix_u[g] = __ldg(prefix + g);
@@ -651,6 +656,30 @@ nms_mask_units_kernel(const typename O::Row* __restrict__ rows, const typename O
           if (lane == (i & 31)) word = bb;
         }
       }
+    } else if (O::FMT != 4 && !zero_hit && AIDET_NMS_COMPACT_PAIRS) {
+      // sparse unit: circle tests for all rows, then every lane walks its own candidates (see nms_fused_kernel)
+      uint32_t cand = 0;
+      for (int i = r0; i < r_end; ++i)
+        if (live && j > i && !O::disjoint(rr[i], me)) cand |= 1u << (i - r0);
+      uint32_t* ww = &s_ww[warp][0];
+      ww[lane] = 0u;
+      __syncwarp();
+      while (cand) {
+        const int k = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const Row& a = rr[r0 + k];
+        const float area_a = O::area(a, one);
+        float inter = O::inter(a, me, one);
+        inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_me));
+        const float den = area_a + area_me - inter;
+        const float rhs = th * den;
+        const bool h = GE ? (inter >= rhs) : (inter > rhs);
+        if (h && den > 0.0f) atomicOr(&ww[k], 1u << lane);
+      }
+      __syncwarp();
+      const int k_mine = (r0 & ~31) + lane - r0;
+      if (k_mine >= 0 && k_mine < r_end - r0) word = ww[k_mine];
+      __syncwarp();
     } else {
 #pragma unroll 2
       for (int i = r0; i < r_end; ++i) {
@@ -909,8 +938,11 @@ constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp u
 constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
 constexpr int kScanHelpers = kFusedThreads / 32 - 2;
 constexpr int kSoloBlocks = 16;           // groups of <= 16 blocks (512 boxes): scanned by one warp from shared memory
+#ifndef AIDET_NMS_UNITS_PER_WARP_LARGE
+#define AIDET_NMS_UNITS_PER_WARP_LARGE 4   // nms_mask_units_kernel: the same rule for the batched path
+#endif
 #ifndef AIDET_NMS_UNITS_PER_WARP
-#define AIDET_NMS_UNITS_PER_WARP 4      // fused kernel: mask units are split finer until each warp has this many
+#define AIDET_NMS_UNITS_PER_WARP 1      // fused kernel: mask units are split finer until each warp has this many
 #endif
 #ifndef AIDET_NMS_FUSED_MINB
 #define AIDET_NMS_FUSED_MINB 2          // fused kernel: resident CTAs per SM the register budget allows (128 registers)
@@ -960,6 +992,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   // phase 2 also stages each warp's unit rows there (8 warps x 32 records behind the tables, 128 B aligned)
   Row* const wrows = reinterpret_cast<Row*>(dyn + (((size_t)(n_groups + 2) * 12 + 127) & ~(size_t)127));
   __shared__ int swarp[kFusedThreads / 32];
+  __shared__ uint32_t s_ww[kFusedThreads];     // phase 2: a warp's 32 row words while its lanes walk their own candidates
   __shared__ __align__(8) uint64_t bar_full[kScanSlotsMax], bar_k[kScanSlotsMax];
   __shared__ uint32_t s_issued;              // blocks whose copy the producer has issued
   __shared__ uint32_t s_hprog[kFusedThreads / 32];            // blocks finished by each helper warp (written by its lane 0 only)
@@ -1205,6 +1238,34 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
             if (lane == (i & 31)) word = bb;
           }
         }
+      } else if (O::FMT != 4 && !zero_hit && AIDET_NMS_COMPACT_PAIRS) {
+        // Sparse unit.  A row costs the warp the full overlap arithmetic as soon as ONE of its 32 columns passes the circle
+        // test, and with 32 columns that is nearly every row even on DOTA-shaped boxes (the unit's columns are neighbours
+        // in score order, not in space).  So: circle tests for all rows first (a candidate bit per row in each lane),
+        // then every lane walks ITS OWN candidates -- the column stays in its registers, the row record comes from the
+        // warp's staged rows -- and the warp runs max-over-lanes(candidates) passes instead of one per row.
+        uint32_t cand = 0;
+        for (int i = r0; i < r_end; ++i)
+          if (live && j > i && !O::disjoint(rr[i], me)) cand |= 1u << (i - r0);
+        uint32_t* ww = s_ww + warp * 32;
+        ww[lane] = 0u;
+        __syncwarp();
+        while (cand) {
+          const int k = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const Row& a = rr[r0 + k];
+          const float area_a = O::area(a, one);
+          float inter = O::inter(a, me, one);
+          inter = fminf(fmaxf(inter, 0.0f), fminf(area_a, area_me));
+          const float den = area_a + area_me - inter;
+          const float rhs = th * den;
+          const bool h = GE ? (inter >= rhs) : (inter > rhs);
+          if (h && den > 0.0f) atomicOr(&ww[k], 1u << lane);
+        }
+        __syncwarp();
+        const int k_mine = (r0 & ~31) + lane - r0;
+        if (k_mine >= 0 && k_mine < r_end - r0) word = ww[k_mine];
+        __syncwarp();
       } else {
 #pragma unroll 2
         for (int i = r0; i < r_end; ++i) {
@@ -1689,7 +1750,7 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     const int resident = sms * (O::FMT == 8 ? 3 : 4);
     const int side = max(1, n / n_groups);
     int rc_rows = 4;                                          // the finest split until there are >= 8 units per warp
-    while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= 8LL * resident * 8) rc_rows <<= 1;
+    while (rc_rows < 32 && (long long)n_groups * fused_units(side, 32 / rc_rows, rc_rows) >= (long long)AIDET_NMS_UNITS_PER_WARP_LARGE * resident * 8) rc_rows <<= 1;
     nms_tile_prefix_kernel<<<1, 1024, 0, s>>>(gstart, gend, n_groups, tile_rows, prefix, rc_rows);
     const int stage = n_groups <= 8192 ? 1 : 0;
     const size_t psmem = stage ? (size_t)(n_groups + 1) * 4 : 0;
