@@ -518,7 +518,7 @@ def run_ours(args, D):
     # ---------------- batched rotated NMS (C2)
     if args.workload in ("all", "nms"):
         nms = {}
-        for tag, dense, images, fmt8 in (("c2", False, 1, False), ("c2_dense", True, 1, False), ("c2x8_dense", True, 8, False),
+        for tag, dense, images, fmt8 in (("c2", False, 1, False), ("c2_dense", True, 1, False), ("c2x8", False, 8, False), ("c2x8_dense", True, 8, False),
                                          ("c2_8point", False, 1, True), ("c2_dense_8point", True, 1, True)):
             cb, cs, cg, ng = nms_inputs(dense=dense, images=images)
             if fmt8:
@@ -840,7 +840,7 @@ def run_ours(args, D):
             ops["iou_8point_free_quads_gpairs_s"] = line["iou_8point"]["free_quads"]["value"]
             ops["iou_8point_free_quads_frac"] = line["iou_8point"]["free_quads"]["roofline_frac"]
         if "nms" in line:
-            for k in ("c2", "c2_dense", "c2x8_dense", "one_group_dense", "c2_8point", "one_group_dense_8point"):
+            for k in ("c2", "c2_dense", "c2x8", "c2x8_dense", "one_group_dense", "c2_8point", "one_group_dense_8point"):
                 if k in line["nms"]:
                     ops["nms_%s_mboxes_s" % k] = line["nms"][k]["value"]
                     ops["nms_%s_whole_call_frac" % k] = line["nms"][k]["roofline"]["frac"]
