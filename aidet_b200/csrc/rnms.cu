@@ -1569,7 +1569,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(done, 1) == (int)gridDim.x - 1);
   __syncthreads();
-  if (!s_last) return;
+  if (!s_last || !keep_out) return;                                   // keep_out == nullptr: the caller only wants the flags
   __threadfence();
   const int per = ((n + kFusedThreads - 1) / kFusedThreads + 15) & ~15;
   const int lo = min(n, tid * per), hi = min(n, lo + per);
@@ -1782,15 +1782,126 @@ static int run_nms(const float* boxes, const float* scores, const int* groups, i
     if (scan_smem > 227 * 1024) { set_error("nms: %d boxes exceed the single-group scan capacity", n); return AIDET_EINVAL; }
     AIDET_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
   }
-  const bool fused_compact = n <= kFusedCompactMax;
+  const bool fused_compact = n <= kFusedCompactMax && keep_out;       // keep_out == nullptr: the caller only wants the flags
   nms_scan_kernel<<<n_groups, 256, scan_smem, s>>>(mask32, L.pitch32, gstart, gend, order, flags, removed_cap, scan_pw,
                                                    n, keep_out, n_keep, fused_compact ? counters + 1 : nullptr);
-  if (!fused_compact) nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
-  count_launch((small ? (local_prefix ? 3 : 4) : 5) + (fused_compact ? 0 : 1));        // + the CUB sort passes, which are library kernels and not counted
+  if (!fused_compact && keep_out) nms_compact_kernel<<<1, 1024, 0, s>>>(flags, n, keep_out, n_keep);
+  count_launch((small ? (local_prefix ? 3 : 4) : 5) + ((fused_compact || !keep_out) ? 0 : 1));        // + the CUB sort passes, which are library kernels and not counted
   AIDET_CUDA(cudaGetLastError());
   return AIDET_OK;
 }
 
+
+// ------------------------------------------------------------------ 7. scene merge (config C5)
+// Per-tile NMS + cross-tile merge NMS of one scene (tools/parse_results.py:56-76 / dota.py:296-327 of the reference do
+// this per class on the host with DOTA_devkit's py_cpu_nms_poly_fast).  Three entry points, one per stage, so that the
+// multi-GPU form can put ONE all-reduce of the keep masks between them; every helper below is one small launch.
+__global__ void __launch_bounds__(256) scene_prepare_kernel(const float* __restrict__ boxes, int fmt, const int* __restrict__ labels,
+                                                            const int* __restrict__ tile_ids, const float* __restrict__ origins,
+                                                            int n, int n_tiles, int n_classes, int world, int rank,
+                                                            int* __restrict__ groups, float* __restrict__ scene) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = tile_ids[i], l = labels[i];
+  const bool valid = t >= 0 && t < n_tiles && l >= 0 && l < n_classes;
+  groups[i] = (valid && (world == 1 || t % world == rank)) ? t * n_classes + l : n_tiles * n_classes;
+  const float ox = valid ? origins[2 * t] : 0.f, oy = valid ? origins[2 * t + 1] : 0.f;
+  const float* b = boxes + (size_t)i * fmt;
+  float* o = scene + (size_t)i * fmt;
+  if (fmt == 5) {
+    o[0] = b[0] + ox; o[1] = b[1] + oy; o[2] = b[2]; o[3] = b[3]; o[4] = b[4];
+  } else {
+    for (int k = 0; k < fmt; k += 2) { o[k] = b[k] + ox; o[k + 1] = b[k + 1] + oy; }
+  }
+}
+
+__global__ void __launch_bounds__(256) scene_merge_groups_kernel(const int* __restrict__ labels, const uint8_t* __restrict__ surv,
+                                                                 int n, int n_classes, int world, int rank, int* __restrict__ groups) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = labels[i];
+  const bool mine = surv[i] && l >= 0 && l < n_classes && (world == 1 || l % world == rank);
+  groups[i] = mine ? l : n_classes;
+}
+
+constexpr int kSceneParts = 16;      // the index range is cut into 16 parts: counts per (part, class), one CTA per (class, part)
+
+__global__ void __launch_bounds__(256) scene_count_kernel(const int* __restrict__ labels, const uint8_t* __restrict__ kept, int n,
+                                                          int n_classes, int part_len, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = (i < n && kept[i]) ? labels[i] : -1;
+  if (l < 0 || l >= n_classes) return;
+  // neighbouring detections mostly share a class (and a part): one atomic per (warp, part, class)
+  const int key = (i / part_len) * n_classes + l;
+  const unsigned peers = __match_any_sync(__activemask(), key);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + key, __popc(peers));
+}
+
+// class c's survivors in ascending original index, behind those of the classes < c: CTA (c, p) compacts part p of the
+// index range for class c; its base comes from the (part, class) counts
+__global__ void __launch_bounds__(1024) scene_compact_kernel(const float* __restrict__ scene, int fmt, const float* __restrict__ scores,
+                                                             const int* __restrict__ labels, const uint8_t* __restrict__ kept, int n,
+                                                             int n_classes, int part_len, const int* __restrict__ counts,
+                                                             float* __restrict__ out_boxes, float* __restrict__ out_scores,
+                                                             int* __restrict__ out_labels, int* __restrict__ out_index,
+                                                             int* __restrict__ n_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_red[32];
+  const int c = blockIdx.x, p = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // base = every kept box of a lower class + those of class c in earlier parts (total = all, for n_out)
+  int mine = 0, all = 0;
+  for (int k = tid; k < kSceneParts * n_classes; k += 1024) {
+    const int v = counts[k], kc = k % n_classes, kp = k / n_classes;
+    all += v;
+    if (kc < c || (kc == c && kp < p)) mine += v;
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine); all = __reduce_add_sync(0xffffffffu, all);
+  if (lane == 0) { s_warp[warp] = mine; s_red[warp] = all; }
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < 32; ++w) { base += s_warp[w]; total += s_red[w]; }
+  if (c == 0 && p == 0 && tid == 0) *n_out = total;
+  __syncthreads();
+  const int lo = p * part_len, hi = min(n, lo + part_len);
+  for (int i0 = lo; i0 < hi; i0 += 1024) {
+    const int i = i0 + tid;
+    const bool f = i < hi && kept[i] && labels[i] == c;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, sum = 0;
+    for (int w = 0; w < 32; ++w) { const int v = s_warp[w]; if (w < warp) before += v; sum += v; }
+    if (f) {
+      const int o = base + before + __popc(bal & ((1u << lane) - 1u));
+      for (int k = 0; k < fmt; ++k) out_boxes[(size_t)o * fmt + k] = scene[(size_t)i * fmt + k];
+      out_scores[o] = scores[i];
+      out_labels[o] = c;
+      out_index[o] = i;
+    }
+    base += sum;
+    __syncthreads();
+  }
+}
+
+struct SceneLayout { size_t nms, groups, keep, small, total; };
+static int scene_layout(int n, int n_groups_max, int fmt, SceneLayout* S, NmsLayout* L, int n_groups) {
+  size_t cub_bytes = 0;
+  if (int rc = cub_temp_bytes(max(n, 1), 64, &cub_bytes)) return rc;
+  const NmsLayout big = nms_layout(max(n, 1), n_groups_max, fmt, cub_bytes);
+  if (L) *L = nms_layout(max(n, 1), n_groups, fmt, cub_bytes);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 128); return o; };
+  S->nms = take(big.total); S->groups = take((size_t)n * 4); S->keep = take((size_t)n * 8); S->small = take(4096 + 8);
+  S->total = off;
+  return AIDET_OK;
+}
+
+template <class F>
+static int scene_dispatch(int fmt, F&& f) {
+  if (fmt == 5) return f(NmsRect{});
+  if (fmt == 8) return f(NmsQuad{});
+  return f(NmsHbb{});
+}
 }  // namespace aidet
 
 using namespace aidet;
@@ -1831,6 +1942,103 @@ int aidet_nms_batched_f32(const float* boxes, int fmt, const float* scores, cons
   if (fmt == 5) return run_nms<NmsRect>(boxes, scores, group_ids, n, thr, n_thr, n_groups, cmp, one, keep_out, n_keep, ws, L, device, s);
   if (fmt == 8) return run_nms<NmsQuad>(boxes, scores, group_ids, n, thr, n_thr, n_groups, cmp, one, keep_out, n_keep, ws, L, device, s);
   return run_nms<NmsHbb>(boxes, scores, group_ids, n, thr, n_thr, n_groups, cmp, one, keep_out, n_keep, ws, L, device, s);
+}
+
+
+size_t aidet_scene_workspace_bytes(int n, int n_tiles, int n_classes, int fmt) {
+  if (n < 0 || n_tiles < 1 || n_classes < 1 || n_classes > 1024 || (fmt != 4 && fmt != 5 && fmt != 8)) return 0;
+  if ((long long)n_tiles * n_classes > (1LL << 24)) return 0;
+  aidet::SceneLayout S;
+  if (aidet::scene_layout(n, n_tiles * n_classes, fmt, &S, nullptr, 1)) return 0;
+  return S.total;
+}
+
+int aidet_scene_tile_nms_f32(const float* boxes, int fmt, const float* scores, const int* labels, const int* tile_ids,
+                             const float* tile_origins, int n, int n_tiles, int n_classes, const float* thr, int world,
+                             int rank, unsigned char* keep_mask, float* scene_boxes, void* workspace, size_t ws_bytes,
+                             int device, void* stream) {
+  using namespace aidet;
+  AIDET_REQUIRE(fmt == 4 || fmt == 5 || fmt == 8, "aidet_scene_tile_nms_f32: fmt must be 4, 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(n >= 0 && n_tiles >= 1 && n_classes >= 1 && n_classes <= 1024, "aidet_scene_tile_nms_f32: bad sizes");
+  AIDET_REQUIRE(world >= 1 && rank >= 0 && rank < world, "aidet_scene_tile_nms_f32: bad world %d / rank %d", world, rank);
+  if (int rc = set_device(device)) return rc;
+  if (n == 0) return AIDET_OK;
+  AIDET_REQUIRE(boxes && scores && labels && tile_ids && tile_origins && thr && keep_mask && scene_boxes && workspace,
+                "aidet_scene_tile_nms_f32: null pointer");
+  AIDET_REQUIRE(((uintptr_t)workspace & 127) == 0, "aidet_scene_tile_nms_f32: workspace must be 128 B aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_groups = n_tiles * n_classes;
+  SceneLayout S; NmsLayout L;
+  if (int rc = scene_layout(n, n_groups, fmt, &S, &L, n_groups)) return rc;
+  if (ws_bytes < S.total) { set_error("aidet_scene_tile_nms_f32: workspace %zu < %zu", ws_bytes, S.total); return AIDET_EWORKSPACE; }
+  char* ws = (char*)workspace;
+  int* groups = (int*)(ws + S.groups);
+  int* n_keep = (int*)(ws + S.small);
+  scene_prepare_kernel<<<ceil_div(n, 256), 256, 0, s>>>(boxes, fmt, labels, tile_ids, tile_origins, n, n_tiles, n_classes, world,
+                                                        rank, groups, scene_boxes);
+  count_launch(1);
+  int rc = scene_dispatch(fmt, [&](auto o) {
+    return run_nms<decltype(o)>(boxes, scores, groups, n, thr, 1, n_groups, AIDET_CMP_GT, 0.0f, nullptr, n_keep, ws + S.nms, L, device, s);
+  });
+  if (rc) return rc;
+  AIDET_CUDA(cudaMemcpyAsync(keep_mask, ws + S.nms + L.flags, (size_t)n, cudaMemcpyDeviceToDevice, s));
+  return AIDET_OK;
+}
+
+int aidet_scene_merge_nms_f32(const float* scene_boxes, int fmt, const float* scores, const int* labels,
+                              const unsigned char* survivors, int n, int n_tiles, int n_classes, const float* merge_thr,
+                              int world, int rank, unsigned char* keep_mask, void* workspace, size_t ws_bytes, int device,
+                              void* stream) {
+  using namespace aidet;
+  AIDET_REQUIRE(fmt == 4 || fmt == 5 || fmt == 8, "aidet_scene_merge_nms_f32: fmt must be 4, 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(n >= 0 && n_tiles >= 1 && n_classes >= 1 && n_classes <= 1024, "aidet_scene_merge_nms_f32: bad sizes");
+  AIDET_REQUIRE(world >= 1 && rank >= 0 && rank < world, "aidet_scene_merge_nms_f32: bad world %d / rank %d", world, rank);
+  if (int rc = set_device(device)) return rc;
+  if (n == 0) return AIDET_OK;
+  AIDET_REQUIRE(scene_boxes && scores && labels && survivors && merge_thr && keep_mask && workspace,
+                "aidet_scene_merge_nms_f32: null pointer");
+  AIDET_REQUIRE(((uintptr_t)workspace & 127) == 0, "aidet_scene_merge_nms_f32: workspace must be 128 B aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  SceneLayout S; NmsLayout L;
+  if (int rc = scene_layout(n, n_tiles * n_classes, fmt, &S, &L, n_classes)) return rc;
+  if (ws_bytes < S.total) { set_error("aidet_scene_merge_nms_f32: workspace %zu < %zu", ws_bytes, S.total); return AIDET_EWORKSPACE; }
+  char* ws = (char*)workspace;
+  int* groups = (int*)(ws + S.groups);
+  int* n_keep = (int*)(ws + S.small);
+  scene_merge_groups_kernel<<<ceil_div(n, 256), 256, 0, s>>>(labels, survivors, n, n_classes, world, rank, groups);
+  count_launch(1);
+  int rc = scene_dispatch(fmt, [&](auto o) {
+    return run_nms<decltype(o)>(scene_boxes, scores, groups, n, merge_thr, n_classes, n_classes, AIDET_CMP_GT, 0.0f, nullptr, n_keep,
+                                ws + S.nms, L, device, s);
+  });
+  if (rc) return rc;
+  AIDET_CUDA(cudaMemcpyAsync(keep_mask, ws + S.nms + L.flags, (size_t)n, cudaMemcpyDeviceToDevice, s));
+  return AIDET_OK;
+}
+
+int aidet_scene_compact_f32(const float* scene_boxes, int fmt, const float* scores, const int* labels,
+                            const unsigned char* kept, int n, int n_classes, float* out_boxes, float* out_scores,
+                            int* out_labels, int* out_index, int* n_out, void* workspace, size_t ws_bytes, int device,
+                            void* stream) {
+  using namespace aidet;
+  AIDET_REQUIRE(fmt == 4 || fmt == 5 || fmt == 8, "aidet_scene_compact_f32: fmt must be 4, 5 or 8, got %d", fmt);
+  AIDET_REQUIRE(n >= 0 && n_classes >= 1 && n_classes <= 1024, "aidet_scene_compact_f32: bad sizes");
+  AIDET_REQUIRE(n_out && workspace && ws_bytes >= (size_t)kSceneParts * n_classes * sizeof(int),
+                "aidet_scene_compact_f32: null pointer / workspace too small");
+  if (int rc = set_device(device)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) { AIDET_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int), s)); return AIDET_OK; }
+  AIDET_REQUIRE(scene_boxes && scores && labels && kept && out_boxes && out_scores && out_labels && out_index,
+                "aidet_scene_compact_f32: null pointer");
+  int* counts = (int*)workspace;
+  const int part_len = ceil_div(n, kSceneParts);
+  AIDET_CUDA(cudaMemsetAsync(counts, 0, (size_t)kSceneParts * n_classes * sizeof(int), s));
+  scene_count_kernel<<<ceil_div(n, 256), 256, 0, s>>>(labels, kept, n, n_classes, part_len, counts);
+  scene_compact_kernel<<<dim3(n_classes, kSceneParts), 1024, 0, s>>>(scene_boxes, fmt, scores, labels, kept, n, n_classes, part_len,
+                                                                     counts, out_boxes, out_scores, out_labels, out_index, n_out);
+  count_launch(2);
+  AIDET_CUDA(cudaGetLastError());
+  return AIDET_OK;
 }
 
 }  // extern "C"

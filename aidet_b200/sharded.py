@@ -187,6 +187,60 @@ def _keep_mask(boxes, scores, groups, thr, n_groups, nms_fn):
     return mask[:n]
 
 
+def _scene_merge_native(boxes, scores, labels, tile_ids, tile_origins, num_classes, tile_iou_thr, merge_thr, world, rank,
+                        group):
+    """scene_merge_nms through the library's three scene entry points (include/aidet_b200.h): group ids, the translation
+    to the scene frame, both NMS stages and the class-major compaction are device code launched from C++ -- 5 small
+    kernels + 2 NMS calls instead of ~30 torch ops whose launch gaps dominated the call.  The only host synchronisation
+    is the read of the output count."""
+    import ctypes as C
+
+    from . import _lib as L
+    from .ops import functional as F
+    lib = L.lib()
+    dev = boxes.device
+    L.require_cuda(boxes, "boxes")
+    n, fmt = boxes.shape
+    if merge_thr.numel() != num_classes:
+        raise ValueError("merge_thr must hold %d thresholds, got %d" % (num_classes, merge_thr.numel()))
+    boxes = boxes.contiguous().float()
+    scores = scores.to(dev).contiguous().float()
+    lab = labels.to(device=dev, dtype=torch.int32).contiguous()
+    tid = tile_ids.to(device=dev, dtype=torch.int32).contiguous()
+    org = tile_origins.to(device=dev, dtype=torch.float32).contiguous()
+    n_tiles = org.size(0)
+    merge_thr = merge_thr.contiguous()
+    nbytes = lib.aidet_scene_workspace_bytes(n, n_tiles, num_classes, fmt)
+    if nbytes == 0:
+        raise ValueError("scene_merge_nms: bad sizes n=%d tiles=%d classes=%d box width %d" % (n, n_tiles, num_classes, fmt))
+    ws = F._nms_workspace(dev, nbytes + 128)
+    wsp = C.c_void_p((ws.data_ptr() + 127) // 128 * 128)
+    stream = L.stream_ptr(dev)
+    surv = torch.empty(n, dtype=torch.uint8, device=dev)
+    sb = torch.empty_like(boxes)
+    L.check(lib.aidet_scene_tile_nms_f32(L.dptr(boxes), fmt, L.dptr(scores), L.dptr(lab), L.dptr(tid), L.dptr(org), n, n_tiles,
+                                         num_classes, L.dptr(F._scalar_thr(tile_iou_thr, dev)), world, rank, L.dptr(surv),
+                                         L.dptr(sb), wsp, nbytes, dev.index, stream), "aidet_scene_tile_nms_f32")
+    if world > 1:
+        dist.all_reduce(surv, group=group)                   # the ranks' masks are disjoint: the sum is their union
+    kept = torch.empty(n, dtype=torch.uint8, device=dev)
+    L.check(lib.aidet_scene_merge_nms_f32(L.dptr(sb), fmt, L.dptr(scores), L.dptr(lab), L.dptr(surv), n, n_tiles, num_classes,
+                                          L.dptr(merge_thr), world, rank, L.dptr(kept), wsp, nbytes, dev.index, stream),
+            "aidet_scene_merge_nms_f32")
+    if world > 1:
+        dist.all_reduce(kept, group=group)
+    out_b = torch.empty_like(sb)
+    out_s = torch.empty_like(scores)
+    out_l = torch.empty(n, dtype=torch.int32, device=dev)
+    out_i = torch.empty(n, dtype=torch.int32, device=dev)
+    n_out = torch.empty(1, dtype=torch.int32, device=dev)
+    L.check(lib.aidet_scene_compact_f32(L.dptr(sb), fmt, L.dptr(scores), L.dptr(lab), L.dptr(kept), n, num_classes, L.dptr(out_b),
+                                        L.dptr(out_s), L.dptr(out_l), L.dptr(out_i), L.dptr(n_out), wsp, nbytes, dev.index,
+                                        stream), "aidet_scene_compact_f32")
+    k = int(n_out.item())
+    return out_b[:k], out_s[:k], out_l[:k].long()
+
+
 def scene_merge_nms(boxes, scores, labels, tile_ids, tile_origins, num_classes=15, tile_iou_thr=0.5, merge_thr=None,
                     group=None, nms_fn=None):
     """Per-tile NMS + cross-tile merge NMS of one scene, tiles sharded over the ranks.
@@ -210,6 +264,9 @@ def scene_merge_nms(boxes, scores, labels, tile_ids, tile_origins, num_classes=1
     if merge_thr is None:
         merge_thr = merge_thresholds('obb')
     merge_thr = merge_thr.to(device=dev, dtype=torch.float32)
+    if nms_fn is None and isinstance(tile_iou_thr, (int, float)):
+        return _scene_merge_native(boxes, scores, labels, tile_ids, tile_origins, num_classes, float(tile_iou_thr),
+                                   merge_thr, world, rank, group)
     labels = labels.long()
     tile_ids = tile_ids.long()
 

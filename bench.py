@@ -180,6 +180,10 @@ def timed(D, dev, steps, warmup, fn, flush=None):
     torch.cuda.synchronize(dev)
     D.barrier()
     torch.cuda.synchronize(dev)
+    import gc
+    gc.collect()
+    gc_was = gc.isenabled()
+    gc.disable()                                             # a collection inside a 70 us step would be charged to it
     l0 = L.launch_count()
     if flush is None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -199,6 +203,8 @@ def timed(D, dev, steps, warmup, fn, flush=None):
         torch.cuda.synchronize(dev)
         ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = L.launch_count() - l0
+    if gc_was:
+        gc.enable()
     D.barrier()
     torch.cuda.synchronize(dev)
     return D.max_float(ms, dev), launches

@@ -133,6 +133,34 @@ int aidet_nms_batched_f32(const float* boxes, int fmt, const float* scores, cons
                           long long* keep_out, int* n_keep, void* workspace, size_t ws_bytes,
                           int device, void* stream);
 
+/* ---- scene merge: per-tile NMS + cross-tile merge NMS of one large scene ------
+ * Replaces: the host loop that merges tile results per class (tools/parse_results.py:56-76, which calls
+ * mmdet/datasets/dota.py:296-327 -> DOTA_devkit py_cpu_nms_poly_fast per class with the thresholds of dota.py:324)
+ * after the per-tile multiclass NMS (mmdet/core/post_processing/bbox_nms.py:32-52 per class).
+ * Three stages, one entry point each, all on `stream` with no host synchronisation; with several GPUs the caller
+ * all-reduces (sums) the keep masks between the stages (`world` ranks: stage 1 takes the tiles t % world == rank,
+ * stage 2 the classes c % world == rank; world = 1, rank = 0 on one GPU).  Suppression is IoU > thr, no +1.
+ *   boxes (n, fmt) tile-frame; labels, tile_ids (n) int32; tile_origins (n_tiles, 2) float32 (x, y) of each tile;
+ *   thr: DEVICE float (per-tile NMS); merge_thr: DEVICE (n_classes) floats; keep_mask / survivors / kept: (n) uint8.
+ * stage 1 writes scene_boxes (n, fmt) = boxes translated by their tile's origin and keep_mask (1 = survives its tile);
+ * stage 2 takes the survivors of ALL ranks and writes keep_mask (1 = survives the merge); the compaction writes the kept
+ *   detections class by class, ascending original index inside a class (one Task1_<class>.txt each, dota.py:296-308),
+ *   into out_* (capacity n) and their number into the device int *n_out.  Labels / tiles out of range are never kept.
+ * workspace: >= aidet_scene_workspace_bytes(n, n_tiles, n_classes, fmt) bytes, 128 B aligned (0 = bad arguments).   */
+size_t aidet_scene_workspace_bytes(int n, int n_tiles, int n_classes, int fmt);
+int aidet_scene_tile_nms_f32(const float* boxes, int fmt, const float* scores, const int* labels, const int* tile_ids,
+                             const float* tile_origins, int n, int n_tiles, int n_classes, const float* thr, int world,
+                             int rank, unsigned char* keep_mask, float* scene_boxes, void* workspace, size_t ws_bytes,
+                             int device, void* stream);
+int aidet_scene_merge_nms_f32(const float* scene_boxes, int fmt, const float* scores, const int* labels,
+                              const unsigned char* survivors, int n, int n_tiles, int n_classes, const float* merge_thr,
+                              int world, int rank, unsigned char* keep_mask, void* workspace, size_t ws_bytes, int device,
+                              void* stream);
+int aidet_scene_compact_f32(const float* scene_boxes, int fmt, const float* scores, const int* labels,
+                            const unsigned char* kept, int n, int n_classes, float* out_boxes, float* out_scores,
+                            int* out_labels, int* out_index, int* n_out, void* workspace, size_t ws_bytes, int device,
+                            void* stream);
+
 /* ---- Soft-NMS (axis-aligned, +1 convention), batched over groups ------------
  * Replaces: soft_nms_cpu_kernel (mmdet/ops/nms/src/nms_cpu.cpp:70-201), the reference's only Soft-NMS -- CUDA
  * tensors are copied to the host and back around it (mmdet/ops/nms/nms_wrapper.py:92-94,110-114).

@@ -47,3 +47,31 @@ def test_c5_pointobb_scene_merge(cuda):
     assert m8[0].shape[1] == 8
     # same detections survive unless a pair sits within f32 rounding of a threshold (8-point inputs are rounded)
     assert abs(m5[0].shape[0] - m8[0].shape[0]) <= 2
+
+
+def test_scene_merge_native_equals_the_composed_calls(cuda):
+    """The library's three scene entry points against the same stages composed from nms_batched in torch (the form
+    the multi-tensor-threshold path still takes): identical outputs, bit for bit."""
+    bx, sc, lb, ti, org = [t.to(cuda) for t in synth.scene_dets(scene=1500, tile=512, overlap=100, dets_per_tile=300, seed=8)]
+    native = sharded.scene_merge_nms(bx, sc, lb, ti, org)
+    composed = sharded.scene_merge_nms(bx, sc, lb, ti, org, tile_iou_thr=torch.tensor([0.5], device=cuda))
+    for a, b in zip(native, composed):
+        assert torch.equal(a, b)
+
+
+def test_scene_merge_empty_and_out_of_range(cuda):
+    bx, sc, lb, ti, org = [t.to(cuda) for t in synth.scene_dets(scene=1200, tile=512, overlap=100, dets_per_tile=150, seed=9)]
+    eb, es, el = sharded.scene_merge_nms(bx[:0], sc[:0], lb[:0], ti[:0], org)
+    assert eb.shape == (0, 5) and es.numel() == 0 and el.numel() == 0
+    # detections whose label or tile id is out of range are never kept and do not disturb the others
+    bad = torch.zeros_like(lb, dtype=torch.bool)
+    bad[::7] = True
+    lb2 = torch.where(bad, torch.full_like(lb, 99), lb)
+    ti2 = ti.clone()
+    ti2[3::11] = -1
+    bad |= ti2 < 0
+    got = sharded.scene_merge_nms(bx, sc, lb2, ti2, org)
+    ok = ~bad
+    want = sharded.scene_merge_nms(bx[ok].contiguous(), sc[ok].contiguous(), lb[ok].contiguous(), ti[ok].contiguous(), org)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
