@@ -1883,15 +1883,18 @@ __global__ void __launch_bounds__(1024) scene_compact_kernel(const float* __rest
   }
 }
 
-struct SceneLayout { size_t nms, groups, keep, small, total; };
-static int scene_layout(int n, int n_groups_max, int fmt, SceneLayout* S, NmsLayout* L, int n_groups) {
+struct SceneLayout { size_t nms, groups, small, total; };
+// n_tile_groups = tiles x classes (stage 1), n_classes (stage 2): the NMS area holds the larger of the two layouts -- not
+// always stage 1's: with <= 8192 boxes the fused kernel pads every group's mask to 32 rows, but only up to 1024 groups
+static int scene_layout(int n, int n_tile_groups, int n_classes, int fmt, SceneLayout* S, NmsLayout* L, int n_groups) {
   size_t cub_bytes = 0;
   if (int rc = cub_temp_bytes(max(n, 1), 64, &cub_bytes)) return rc;
-  const NmsLayout big = nms_layout(max(n, 1), n_groups_max, fmt, cub_bytes);
+  const size_t nms_bytes = std::max(nms_layout(max(n, 1), n_tile_groups, fmt, cub_bytes).total,
+                                    nms_layout(max(n, 1), n_classes, fmt, cub_bytes).total);
   if (L) *L = nms_layout(max(n, 1), n_groups, fmt, cub_bytes);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 128); return o; };
-  S->nms = take(big.total); S->groups = take((size_t)n * 4); S->keep = take((size_t)n * 8); S->small = take(4096 + 8);
+  S->nms = take(nms_bytes); S->groups = take((size_t)n * 4); S->small = take(4096 + 8);
   S->total = off;
   return AIDET_OK;
 }
@@ -1949,7 +1952,7 @@ size_t aidet_scene_workspace_bytes(int n, int n_tiles, int n_classes, int fmt) {
   if (n < 0 || n_tiles < 1 || n_classes < 1 || n_classes > 1024 || (fmt != 4 && fmt != 5 && fmt != 8)) return 0;
   if ((long long)n_tiles * n_classes > (1LL << 24)) return 0;
   aidet::SceneLayout S;
-  if (aidet::scene_layout(n, n_tiles * n_classes, fmt, &S, nullptr, 1)) return 0;
+  if (aidet::scene_layout(n, n_tiles * n_classes, n_classes, fmt, &S, nullptr, 1)) return 0;
   return S.total;
 }
 
@@ -1969,7 +1972,7 @@ int aidet_scene_tile_nms_f32(const float* boxes, int fmt, const float* scores, c
   cudaStream_t s = (cudaStream_t)stream;
   const int n_groups = n_tiles * n_classes;
   SceneLayout S; NmsLayout L;
-  if (int rc = scene_layout(n, n_groups, fmt, &S, &L, n_groups)) return rc;
+  if (int rc = scene_layout(n, n_groups, n_classes, fmt, &S, &L, n_groups)) return rc;
   if (ws_bytes < S.total) { set_error("aidet_scene_tile_nms_f32: workspace %zu < %zu", ws_bytes, S.total); return AIDET_EWORKSPACE; }
   char* ws = (char*)workspace;
   int* groups = (int*)(ws + S.groups);
@@ -2000,7 +2003,7 @@ int aidet_scene_merge_nms_f32(const float* scene_boxes, int fmt, const float* sc
   AIDET_REQUIRE(((uintptr_t)workspace & 127) == 0, "aidet_scene_merge_nms_f32: workspace must be 128 B aligned");
   cudaStream_t s = (cudaStream_t)stream;
   SceneLayout S; NmsLayout L;
-  if (int rc = scene_layout(n, n_tiles * n_classes, fmt, &S, &L, n_classes)) return rc;
+  if (int rc = scene_layout(n, n_tiles * n_classes, n_classes, fmt, &S, &L, n_classes)) return rc;
   if (ws_bytes < S.total) { set_error("aidet_scene_merge_nms_f32: workspace %zu < %zu", ws_bytes, S.total); return AIDET_EWORKSPACE; }
   char* ws = (char*)workspace;
   int* groups = (int*)(ws + S.groups);

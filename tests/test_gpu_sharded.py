@@ -75,3 +75,14 @@ def test_scene_merge_empty_and_out_of_range(cuda):
     want = sharded.scene_merge_nms(bx[ok].contiguous(), sc[ok].contiguous(), lb[ok].contiguous(), ti[ok].contiguous(), org)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_scene_merge_many_tiles_few_boxes(cuda):
+    """<= 8192 boxes over more than 1024 tile x class groups: stage 1 takes the multi-kernel path, stage 2 (15 groups) the
+    fused kernel, whose padded mask is the LARGER workspace layout of the two."""
+    bx, sc, lb, ti, org = [t.to(cuda) for t in synth.scene_dets(scene=4400, tile=512, overlap=100, dets_per_tile=30, seed=12)]
+    assert org.shape[0] * 15 > 1024 and bx.shape[0] <= 8192
+    native = sharded.scene_merge_nms(bx, sc, lb, ti, org)
+    composed = sharded.scene_merge_nms(bx, sc, lb, ti, org, tile_iou_thr=torch.tensor([0.5], device=cuda))
+    for a, b in zip(native, composed):
+        assert torch.equal(a, b)
