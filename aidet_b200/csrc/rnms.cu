@@ -931,12 +931,13 @@ constexpr int kFusedMaxGroups = 1024;
 #define AIDET_NMS_PRODUCER_SLEEP __nanosleep(64)
 #endif
 #ifndef AIDET_NMS_FUSED_THREADS
-#define AIDET_NMS_FUSED_THREADS 256
+#define AIDET_NMS_FUSED_THREADS 512
 #endif
 constexpr int kFusedThreads = AIDET_NMS_FUSED_THREADS;
 constexpr int kFusedUnitBoxes = 8;         // boxes ranked + prepared per warp unit
 constexpr int kScanSlotsMax = 32;          // mbarrier slots (blocks in flight <= ring capacity / block size <= 32)
-constexpr int kScanHelpers = kFusedThreads / 32 - 2;
+constexpr int kScanHelpers = 6;              // helper warps 2 .. 7 of the scan (further warps of a larger CTA sit the scan out)
+static_assert(kFusedThreads / 32 >= 2 + kScanHelpers, "the fused kernel needs 8 warps");
 constexpr int kSoloBlocks = 16;           // groups of <= 16 blocks (512 boxes): scanned by one warp from shared memory
 #ifndef AIDET_NMS_UNITS_PER_WARP_LARGE
 #define AIDET_NMS_UNITS_PER_WARP_LARGE 4   // nms_mask_units_kernel: the same rule for the batched path
@@ -945,10 +946,10 @@ constexpr int kSoloBlocks = 16;           // groups of <= 16 blocks (512 boxes):
 #define AIDET_NMS_UNITS_PER_WARP 1      // fused kernel: mask units are split finer until each warp has this many
 #endif
 #ifndef AIDET_NMS_FUSED_MINB
-#define AIDET_NMS_FUSED_MINB 2          // fused kernel: resident CTAs per SM the register budget allows (128 registers)
+#define AIDET_NMS_FUSED_MINB 1          // fused kernel: resident CTAs per SM the register budget allows (512 threads x 128 registers)
 #endif
 #ifndef AIDET_NMS_FUSED_CTAS
-#define AIDET_NMS_FUSED_CTAS 2          // fused kernel: CTAs per SM (the grid barriers cost grows with the CTA count)
+#define AIDET_NMS_FUSED_CTAS 1          // fused kernel: CTAs per SM (the grid barriers cost grows with the CTA count)
 #endif
 #ifndef AIDET_NMS_P1_WAVES
 #define AIDET_NMS_P1_WAVES 2            // CTAs per SM that take part in the fused kernel's ranking phase
@@ -972,9 +973,10 @@ __device__ __forceinline__ int bucket_group(const int* __restrict__ groups, int 
   return (int)min(g, (uint32_t)n_groups);     // ids outside [0, n_groups) go to a bucket behind every group: never scanned
 }
 
-// 2 CTAs per SM with up to 128 registers: measured against 3 and 4 CTAs of 64 / 80 registers (round 3), the two grid
-// barriers cost 1.8 + 2.5 us with 296 CTAs against 3.5 + 5.5 us with 592, and the overlap arithmetic no longer spills;
-// config C2 went from 43 to 35 us per call, C1 from 74 to 66 us
+// ONE CTA of 512 threads per SM with up to 128 registers.  The two grid barriers cost 1.5 + 2.2 us with 148 CTAs, 1.8 + 2.5
+// with 296 and 3.5 + 5.5 with 592 (4 CTAs of 256 threads and 64 registers, where the overlap arithmetic also spilled);
+// measured at config C2 43 -> 35 us per call for 592 -> 296 CTAs and another ~1.2 us of phase time for 296 -> 148, at C1
+// 74 -> 66 -> 64 us.  Warps 8 .. 15 sit the scan phase out (six helper warps are enough; fourteen were slower).
 template <class O, bool GE>
 __global__ void __launch_bounds__(kFusedThreads, AIDET_NMS_FUSED_MINB)
 nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ groups,
@@ -1459,7 +1461,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
         slot = slot_n; par = par_n;
       }
       if (diag && lane == 0) { stamps[11] = t_chain_wait; stamps[12] = nhw; }
-    } else {
+    } else if (warp < 2 + kScanHelpers) {
       // ---- helpers: warp hw owns the words w = hw + kScanHelpers * i; lane (i % 32) keeps the accumulator of its i-th
       //      word in a register (two per lane cover nhw <= 256) and publishes it when the word's last block is done
       const int hw = warp - 2;
