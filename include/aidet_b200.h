@@ -126,7 +126,8 @@ int aidet_assign_wrt_overlaps_f32(const float* overlaps, int m, int n, long long
  *   thr: n_thr == 1 (shared) or n_thr == n_groups (per group, dota.py:324);
  *   plus_one: legacy +1 pixel convention, fmt 4 only (nms_kernel.cu:17-21);
  *   keep_out (n) int64, ascending ORIGINAL index (nms_kernel.cu:135-138);
- *   n_keep: device int32 scalar.                                              */
+ *   n_keep: int32 scalar the device can write: device memory, or pinned host memory that the host polls
+ *           (the kernels only ever store to it, once, when the list is complete).                       */
 size_t aidet_nms_workspace_bytes(int n, int n_groups, int fmt);
 int aidet_nms_batched_f32(const float* boxes, int fmt, const float* scores, const int* group_ids,
                           int n, const float* thr, int n_thr, int n_groups, int cmp, int plus_one,
