@@ -18,6 +18,8 @@
 //   3. scan    one CTA per group walks the rows in score order (greedy), entirely on device
 //   4. compact kept flags -> ascending original indices (nms_kernel.cu:135-138 semantics), done by whichever scan CTA
 //              finishes last
+// Scene form (section 7): per-tile NMS + cross-tile merge NMS of one scene and the class-major compaction, three entry
+// points around the same kernels (aidet_scene_*).
 // Bound: the mask, FP32 issue (same pair arithmetic as riou.cu); everything else is latency.
 #include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -1045,7 +1047,7 @@ nms_fused_kernel(const float* __restrict__ boxes, const float* __restrict__ scor
     // before the first key is built (a plain loop exposes one L2 latency per iteration: 23 of them at config C2)
     uint64_t* skeys = reinterpret_cast<uint64_t*>(dyn);
     const int u_box = (n + kRankBoxes - 1) / kRankBoxes, u_all = u_box + n_groups + 1;
-    // only the first wave of CTAs (one per SM: they start together and have the SM to themselves) takes part
+    // p1_ctas CTAs take part (all of them with one CTA per SM; the knob dates from grids of several CTAs per SM)
     const int ctas_p1 = min(p1_ctas, (u_all + kWarps - 1) / kWarps);
     if (blockIdx.x == 0 && tid == 0) { *done = 0; *ticket = 0; }
     if ((int)blockIdx.x < ctas_p1) {
